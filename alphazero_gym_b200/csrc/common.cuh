@@ -1,0 +1,127 @@
+// common.cuh -- table layouts, kernel parameter block and Philox for the batched MCTS engine (sm_100a).
+//
+// Data layout in HBM.  Trees are independent; everything is indexed tree-major
+// (tree t owns rows [t*R, (t+1)*R), R = max_rollouts + 2).  The reference's pointer-linked
+// Node / Action objects (alphazero/search/states.py:8-112) become:
+//   * one packed HOT row per node, sized to DRAM sectors so a random node visit costs whole sectors
+//     only: 64 B for the discrete tree (node + its A=2 edges), 32 B for the continuous tree (edge + the
+//     child node it leads to -- edges and non-root nodes are 1:1);
+//   * COLD structure-of-arrays side tables that select/backup never touch: env state, cached policy
+//     head, and (continuous) a byte-per-row parent array that is scanned coalesced to enumerate children.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AZG_MAX_K 8
+#define AZG_PENDULUM_R_SCALE 16.2736044 /* mcts.py:20 */
+
+// ---- hot rows ----------------------------------------------------------------------------------
+struct __align__(16) DRow {  // NodeDiscrete + its ActionDiscrete[2]   (states.py:115-191, :292-362)
+    double W[2];             // Action.W
+    double r;                // Node.r
+    int32_t n_e[2];          // Action.n
+    float prior[2];          // Node.priors
+    float V;                 // Node.V (0 for terminal nodes, mcts.py:406-410)
+    int32_t node_n;          // Node.n
+    uint16_t child[2];       // Action.child_node (DROW_NONE if absent)
+    uint16_t parent;         // Node.parent_action.parent_node
+    uint8_t paction;         // Node.parent_action.action
+    uint8_t flags;           // ROW_TERMINAL
+    uint32_t pad[2];
+};
+static_assert(sizeof(DRow) == 64, "discrete row must be two 32 B sectors");
+#define DROW_NONE 0xFFFFu
+
+struct __align__(16) CRow {  // ActionContinuous + the NodeContinuous it leads to (states.py:194-289, :365-433)
+    double W;                // Action.W
+    double r;                // child Node.r (already / PENDULUM_R_SCALE)
+    float V;                 // child Node.V
+    float action;            // Action.action
+    int32_t n_e;             // Action.n
+    uint32_t nn_flags;       // child Node.n in bits 0..23 | CROW_EXPANDED | CROW_TERMINAL
+};
+static_assert(sizeof(CRow) == 32, "continuous row must be one 32 B sector");
+#define ROW_TERMINAL 1u
+#define CROW_NMASK 0x00FFFFFFu
+#define CROW_EXPANDED 0x01000000u
+#define CROW_TERMINAL 0x02000000u
+#define CPARENT_NONE 0xFFu
+
+// leaf word handed from the tree kernels to the evaluation kernel
+#define LEAF_ROW_MASK 0xFFFF
+#define LEAF_EVAL (1 << 29)      // the leaf is new: evaluate it
+#define LEAF_TERMINAL (1 << 30)  // V is forced to 0
+
+#define ERR_NAN 1
+#define ERR_CAPACITY 2
+
+struct TreeParams {
+    int32_t B, R, A, K, HS;  // trees, rows per tree, actions, mixture components, head stride (floats)
+    int32_t puct_f32, v_target, use_tape;
+    double c_uct, gamma, epsilon;
+    float gamma_f32, action_bound;
+    uint64_t seed;
+    int64_t tree_id0;
+    // discrete tables
+    DRow* drows;      // [B][R]
+    double* dstate;   // [B][R][4]
+    // continuous tables
+    CRow* crows;      // [B][R]
+    double2* cstate;  // [B][R]   (th, thdot)
+    float* chead;     // [B][R][HS]  mu[K], sigma[K], prob[K]
+    uint8_t* cparent; // [B][PSTRIDE]
+    int32_t PSTRIDE;
+    const int32_t* pw_table;  // [max_rollouts + 2]  ceil(c_pw * (n+1)^kappa), built on the host
+    // per-tree scalars
+    int32_t* n_rows;  // rows / nodes in use
+    int32_t* draws;   // selection RNG draw counter (stream 0)
+    int32_t* pw;      // progressive-widening insert counter (stream 1 index)
+    int32_t* depth;   // length of the recorded path
+    int32_t* leaf;    // LEAF_* word
+    uint8_t* path;    // [B][R] rows visited by the current simulation (continuous)
+    uint32_t* ctr;    // [4][B]: levels, children scanned, terminal-leaf sims, evals
+    float4* X;        // [B] network input of the leaf
+    const double* root_state;
+    const int32_t* root_n_init;
+    int32_t* err;
+    // evaluator injection (parity level A)
+    const float* tapeV;
+    const float* tapeP;
+    const float* tapeA;
+};
+
+// ---- Philox4x32-10 (Salmon et al. SC'11); counter layout documented in DESIGN.md section 5 ---------
+struct u32x4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        u32x4 n;
+        n.x = hi1 ^ c.y ^ k0;
+        n.y = lo1;
+        n.z = hi0 ^ c.w ^ k1;
+        n.w = lo0;
+        c = n;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ u32x4 rng_block(uint64_t seed, int64_t tree, int stream, int64_t idx, int block) {
+    u32x4 c;
+    c.x = (uint32_t)idx;
+    c.y = (uint32_t)((uint64_t)idx >> 32) ^ ((uint32_t)block << 16);
+    c.z = (uint32_t)tree;
+    c.w = (uint32_t)((uint64_t)tree >> 32) ^ ((uint32_t)stream << 24);
+    return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// stream 0: random.random() / random.choice / random.randint replacements (helpers.py:51, mcts.py:190-192)
+__device__ __forceinline__ uint32_t rng_select_u32(const TreeParams& p, int64_t tree, int draw) {
+    return rng_block(p.seed, tree, 0, draw, 0).x;
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+__device__ __forceinline__ int u32_to_index(uint32_t x, int n) { return (int)__umulhi(x, (uint32_t)n); }

@@ -1,0 +1,676 @@
+// engine.cu -- C ABI (include/azg.h) and kernel orchestration of the batched MCTS engine.
+//
+// One search = init -> evaluate(root) -> [continuous: root widening insert] ->
+//              N x { step<backup of previous sim, select, expand> -> evaluate(leaves) } -> final backup.
+// Trees are independent, so there is no inter-CTA synchronisation anywhere; the 2N+3 launches of a search
+// are captured once into a CUDA graph per (B, n_rollouts, tape, tree_id0) and replayed.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/azg.h"
+#include "common.cuh"
+#include "env.cuh"
+#include "mlp.cuh"
+#include "tree_continuous.cuh"
+#include "tree_discrete.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t _e = (call);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail(AZG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +  \
+                                       std::to_string(__LINE__) + ")");                                      \
+    } while (0)
+
+struct azg_engine {
+    azg_config cfg;
+    int R = 0, HS = 0, P = 0, PO_PAD = 0, L = 0, PW = 0, PSTRIDE = 0, cmax = 0, K3 = 0;
+    int64_t n_weights = 0;
+    int wcount = 0;
+    size_t mlp_smem = 0;
+    int sm_count = 0;
+    // device memory
+    DRow* drows = nullptr;
+    double* dstate = nullptr;
+    CRow* crows = nullptr;
+    double2* cstate = nullptr;
+    float* chead = nullptr;
+    uint8_t* cparent = nullptr;
+    int32_t *pw_table = nullptr, *n_rows = nullptr, *draws = nullptr, *pw = nullptr, *depth = nullptr, *leaf = nullptr;
+    uint8_t* path = nullptr;
+    uint32_t* ctr = nullptr;
+    float4* X = nullptr;
+    double* root_state = nullptr;
+    int32_t* root_n_init = nullptr;
+    int32_t* err = nullptr;
+    float* wpack = nullptr;
+    // results staging (device) + pinned host staging for the *_host entry point
+    float* r_actions = nullptr;
+    int32_t* r_counts = nullptr;
+    double* r_Q = nullptr;
+    double* r_Vt = nullptr;
+    int32_t* r_nchild = nullptr;
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    // tapes
+    const float *tapeV = nullptr, *tapeP = nullptr, *tapeA = nullptr;
+    bool weights_set = false;
+    // last search
+    int last_B = 0, last_N = 0;
+    int64_t launches = 0;
+    std::map<std::tuple<int, int, int, int64_t, int>, cudaGraphExec_t> graphs;
+};
+
+static int head_dim_of(const azg_config& c) {
+    if (c.variant == AZG_DISCRETE) return c.num_actions;
+    return c.num_components > 1 ? 3 * c.num_components : 2;
+}
+
+static int pw_limit(double c_pw, double kappa, int n) { return (int)std::ceil(c_pw * std::pow((double)(n + 1), kappa)); }
+
+extern "C" const char* azg_last_error(void) { return g_err.c_str(); }
+extern "C" const char* azg_version(void) { return "azg 0.1 (sm_100a)"; }
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) {
+    return cudaMalloc((void**)p, n * sizeof(T));
+}
+
+extern "C" void azg_destroy(azg_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+    void* ptrs[] = {e->drows, e->dstate, e->crows, e->cstate, e->chead, e->cparent, e->pw_table, e->n_rows, e->draws, e->pw,
+                    e->depth, e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->r_actions,
+                    e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
+    for (void* q : ptrs)
+        if (q) cudaFree(q);
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
+    if (!cfg || !out) return fail(AZG_EINVAL, "null argument");
+    *out = nullptr;
+    const azg_config& c = *cfg;
+    if (c.variant != AZG_DISCRETE && c.variant != AZG_CONTINUOUS) return fail(AZG_EINVAL, "variant must be AZG_DISCRETE or AZG_CONTINUOUS");
+    if (c.max_rollouts < 1 || c.max_trees < 1) return fail(AZG_EINVAL, "max_rollouts and max_trees must be >= 1");
+    if (c.hidden != 128 && c.hidden != 64) return fail(AZG_EINVAL, "hidden width must be 64 or 128 (weights are staged in shared memory)");
+    if (c.n_hidden < 1 || c.n_hidden > 4) return fail(AZG_EINVAL, "n_hidden must be in 1..4");
+    if (c.activation != AZG_ACT_RELU && c.activation != AZG_ACT_ELU) return fail(AZG_EINVAL, "activation must be relu or elu");
+    if (c.variant == AZG_DISCRETE) {
+        if (c.num_actions != 2 || c.state_dim != 4)
+            return fail(AZG_EINVAL, "discrete variant is CartPole: num_actions must be 2 and state_dim 4");
+        if (c.max_rollouts + 2 > 65534) return fail(AZG_EINVAL, "max_rollouts too large for 16-bit child links");
+    } else {
+        if (c.state_dim != 3) return fail(AZG_EINVAL, "continuous variant is Pendulum: state_dim must be 3");
+        if (c.num_components < 1 || c.num_components > AZG_MAX_K) return fail(AZG_EINVAL, "num_components must be in 1..8");
+        if (c.max_rollouts + 2 > 255) return fail(AZG_EINVAL, "continuous variant supports n_rollouts <= 253 (byte parent links)");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(AZG_ECUDA, "no CUDA device: the engine has no CPU fallback");
+    if (c.device < 0 || c.device >= ndev) return fail(AZG_EINVAL, "bad device ordinal");
+    CK(cudaSetDevice(c.device));
+    azg_engine* e = new azg_engine();
+    e->cfg = c;
+    e->R = c.max_rollouts + 2;
+    e->P = head_dim_of(c);
+    e->PO_PAD = ((1 + e->P) + 3) / 4 * 4;
+    e->K3 = 3 * (c.num_components > 0 ? c.num_components : 1);
+    e->HS = (e->K3 + 3) / 4 * 4;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    e->sm_count = prop.multiProcessorCount;
+    const int H = c.hidden;
+    int64_t nw = (int64_t)c.state_dim * H + H;
+    for (int l = 1; l < c.n_hidden; ++l) nw += (int64_t)H * H + H;
+    nw += H + 1 + (int64_t)e->P * H + e->P;
+    e->n_weights = nw;
+    e->wcount = c.state_dim * H + H + (c.n_hidden - 1) * (H * H + H) + H * e->PO_PAD + e->PO_PAD;
+    e->mlp_smem = ((size_t)e->wcount + (size_t)H * MLP_TM + (size_t)e->PO_PAD * MLP_TM) * sizeof(float);
+    if (e->mlp_smem > (size_t)prop.sharedMemPerBlockOptin) {
+        delete e;
+        return fail(AZG_EINVAL, "network does not fit in shared memory");
+    }
+    const size_t B = c.max_trees, R = e->R;
+    std::vector<int32_t> pwt;
+    if (c.variant == AZG_CONTINUOUS) {
+        int cm = 1;
+        for (int n = 0; n < c.max_rollouts + 2; ++n) {
+            pwt.push_back(pw_limit(c.c_pw, c.kappa, n));
+            if (n <= c.max_rollouts) cm = std::max(cm, pwt.back());
+        }
+        e->cmax = cm + 1;
+        // sub-warp width: enough lanes for the widest child list and for the parent bytes (4*PW rows per lane)
+        int L = 8;
+        while (L < cm) L *= 2;
+        int PW = 1;
+        while (L * 4 * PW < (int)R && PW < 4) PW *= 2;
+        while (L * 4 * PW < (int)R && L < 32) L *= 2;
+        if (L > 32 || L * 4 * PW < (int)R || cm > L) {
+            delete e;
+            return fail(AZG_ECAPACITY, "progressive-widening fan-out or row count exceeds a warp (c_pw/kappa/n_rollouts too large)");
+        }
+        e->L = L;
+        e->PW = PW;
+        e->PSTRIDE = L * 4 * PW;
+    } else {
+        e->cmax = c.num_actions;
+    }
+#define ALLOC(ptr, n)                                   \
+    do {                                                \
+        cudaError_t _e = dalloc(&e->ptr, (n));          \
+        if (_e != cudaSuccess) {                        \
+            std::string m = cudaGetErrorString(_e);     \
+            azg_destroy(e);                             \
+            return fail(AZG_ECUDA, "cudaMalloc " #ptr ": " + m); \
+        }                                               \
+    } while (0)
+    if (c.variant == AZG_DISCRETE) {
+        ALLOC(drows, B * R);
+        ALLOC(dstate, B * R * 4);
+    } else {
+        ALLOC(crows, B * R);
+        ALLOC(cstate, B * R);
+        ALLOC(chead, B * R * e->HS);
+        ALLOC(cparent, B * e->PSTRIDE);
+        ALLOC(pw_table, pwt.size());
+        ALLOC(path, B * R);
+        CK(cudaMemcpy(e->pw_table, pwt.data(), pwt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemset(e->chead, 0, B * R * e->HS * sizeof(float)));
+    }
+    ALLOC(n_rows, B); ALLOC(draws, B); ALLOC(pw, B); ALLOC(depth, B); ALLOC(leaf, B);
+    ALLOC(ctr, 4 * B);
+    ALLOC(X, B);
+    ALLOC(root_state, B * 4);
+    ALLOC(root_n_init, B);
+    ALLOC(err, 1);
+    ALLOC(wpack, (size_t)e->wcount);
+    ALLOC(r_actions, B * e->cmax); ALLOC(r_counts, B * e->cmax); ALLOC(r_Q, B * e->cmax); ALLOC(r_Vt, B); ALLOC(r_nchild, B);
+#undef ALLOC
+    CK(cudaMemset(e->err, 0, sizeof(int32_t)));
+    CK(cudaMemset(e->n_rows, 0, B * sizeof(int32_t)));
+    CK(cudaMemset(e->ctr, 0, 4 * B * sizeof(uint32_t)));
+    CK(cudaFuncSetAttribute(k_mlp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    CK(cudaFuncSetAttribute(k_mlp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    e->h_pinned_bytes = B * 4 * sizeof(double) + B * sizeof(int32_t) +
+                        B * e->cmax * (sizeof(float) + sizeof(int32_t) + sizeof(double)) + B * (sizeof(double) + sizeof(int32_t)) + 256;
+    CK(cudaMallocHost(&e->h_pinned, e->h_pinned_bytes));
+    CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    *out = e;
+    return AZG_OK;
+}
+
+extern "C" int64_t azg_num_weights(const azg_engine* e) { return e ? e->n_weights : 0; }
+extern "C" int32_t azg_cmax(const azg_engine* e) { return e ? e->cmax : 0; }
+extern "C" int32_t azg_rows(const azg_engine* e) { return e ? e->R : 0; }
+extern "C" int32_t azg_head_dim(const azg_engine* e) {
+    if (!e) return 0;
+    return e->cfg.variant == AZG_DISCRETE ? e->cfg.num_actions : e->K3;
+}
+
+// state_dict order -> packed k-major layout consumed by k_mlp
+static void pack_weights(const azg_engine* e, const float* w, std::vector<float>& out) {
+    const int H = e->cfg.hidden, S = e->cfg.state_dim, L = e->cfg.n_hidden, P = e->P, PO = e->PO_PAD;
+    out.assign(e->wcount, 0.0f);
+    float* d = out.data();
+    for (int l = 0; l < L; ++l) {
+        const int K = l == 0 ? S : H;
+        for (int j = 0; j < H; ++j)
+            for (int k = 0; k < K; ++k) d[(size_t)k * H + j] = w[(size_t)j * K + k];
+        d += (size_t)K * H;
+        w += (size_t)K * H;
+        memcpy(d, w, H * sizeof(float));
+        d += H;
+        w += H;
+    }
+    const float* wv = w;            // value_head.weight [1][H]
+    const float* bv = w + H;        // value_head.bias [1]
+    const float* wd = w + H + 1;    // dist_head.weight [P][H]
+    const float* bd = wd + (size_t)P * H;
+    for (int k = 0; k < H; ++k) {
+        d[(size_t)k * PO] = wv[k];
+        for (int q = 0; q < P; ++q) d[(size_t)k * PO + 1 + q] = wd[(size_t)q * H + k];
+    }
+    d += (size_t)H * PO;
+    d[0] = bv[0];
+    for (int q = 0; q < P; ++q) d[1 + q] = bd[q];
+}
+
+extern "C" int azg_set_weights(azg_engine* e, const float* flat, int64_t n, void* stream) {
+    if (!e || !flat) return fail(AZG_EINVAL, "null argument");
+    if (n != e->n_weights) return fail(AZG_EINVAL, "weight count " + std::to_string(n) + " != expected " + std::to_string(e->n_weights));
+    CK(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<float> host(n);
+    cudaPointerAttributes at;
+    bool on_device = cudaPointerGetAttributes(&at, flat) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+    cudaGetLastError();
+    if (on_device) {
+        CK(cudaMemcpyAsync(host.data(), flat, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        memcpy(host.data(), flat, n * sizeof(float));
+    }
+    std::vector<float> packed;
+    pack_weights(e, host.data(), packed);
+    CK(cudaMemcpyAsync(e->wpack, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    e->weights_set = true;
+    return AZG_OK;
+}
+
+extern "C" int azg_set_tapes(azg_engine* e, const float* d_V, const float* d_prior, const float* d_action) {
+    if (!e) return fail(AZG_EINVAL, "null engine");
+    if (d_V) {
+        if (e->cfg.variant == AZG_DISCRETE && !d_prior) return fail(AZG_EINVAL, "discrete tapes need priors");
+        if (e->cfg.variant == AZG_CONTINUOUS && !d_action) return fail(AZG_EINVAL, "continuous tapes need actions");
+    }
+    e->tapeV = d_V;
+    e->tapeP = d_V ? d_prior : nullptr;
+    e->tapeA = d_V ? d_action : nullptr;
+    return AZG_OK;
+}
+
+static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
+    TreeParams p;
+    memset(&p, 0, sizeof p);
+    const azg_config& c = e->cfg;
+    p.B = B; p.R = e->R; p.A = c.num_actions; p.K = c.num_components; p.HS = e->HS;
+    p.puct_f32 = c.puct_f32; p.v_target = c.v_target; p.use_tape = e->tapeV != nullptr;
+    p.c_uct = c.c_uct; p.gamma = c.gamma; p.epsilon = c.epsilon;
+    p.gamma_f32 = (float)c.gamma; p.action_bound = c.action_bound;
+    p.seed = c.seed; p.tree_id0 = tree_id0;
+    p.drows = e->drows; p.dstate = e->dstate;
+    p.crows = e->crows; p.cstate = e->cstate; p.chead = e->chead; p.cparent = e->cparent; p.PSTRIDE = e->PSTRIDE;
+    p.pw_table = e->pw_table;
+    p.n_rows = e->n_rows; p.draws = e->draws; p.pw = e->pw; p.depth = e->depth; p.leaf = e->leaf; p.path = e->path;
+    p.ctr = e->ctr; p.X = e->X; p.root_state = e->root_state; p.root_n_init = e->root_n_init; p.err = e->err;
+    p.tapeV = e->tapeV; p.tapeP = e->tapeP; p.tapeA = e->tapeA;
+    return p;
+}
+
+static MlpParams make_mlp_params(const azg_engine* e, int n) {
+    MlpParams m;
+    memset(&m, 0, sizeof m);
+    const azg_config& c = e->cfg;
+    m.wpack = e->wpack; m.wcount = e->wcount; m.S = c.state_dim; m.L = c.n_hidden; m.P = e->P; m.PO_PAD = e->PO_PAD;
+    m.act = c.activation; m.n = n; m.X = reinterpret_cast<const float*>(e->X); m.xstride = 4; m.mode = 0;
+    m.variant = c.variant; m.A = c.num_actions; m.K = c.num_components; m.R = e->R; m.HS = e->HS;
+    m.ls_min = c.log_std_min; m.ls_max = c.log_std_max;
+    m.leaf = e->leaf; m.drows = e->drows; m.crows = e->crows; m.chead = e->chead; m.evals = e->ctr + (size_t)3 * n;
+    m.head_dim = azg_head_dim(e);
+    return m;
+}
+
+static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStream_t st) {
+    const int tiles = (m.n + MLP_TM - 1) / MLP_TM;
+    const int grid = std::max(1, std::min(tiles, e->sm_count));
+    if (e->cfg.hidden == 128) k_mlp<128><<<grid, (MLP_TM / 8) * (128 / 8), e->mlp_smem, st>>>(m);
+    else k_mlp<64><<<grid, (MLP_TM / 8) * (64 / 8), e->mlp_smem, st>>>(m);
+    return cudaGetLastError();
+}
+
+template <bool BK, bool SEL>
+static cudaError_t launch_step_continuous(const azg_engine* e, const TreeParams& p, cudaStream_t st) {
+    const int grid = (p.B + TREES_PER_CTA - 1) / TREES_PER_CTA;
+    if (e->L == 8 && e->PW == 1) k_step_continuous<8, 1, BK, SEL><<<grid, TREES_PER_CTA * 8, 0, st>>>(p);
+    else if (e->L == 8 && e->PW == 2) k_step_continuous<8, 2, BK, SEL><<<grid, TREES_PER_CTA * 8, 0, st>>>(p);
+    else if (e->L == 8 && e->PW == 4) k_step_continuous<8, 4, BK, SEL><<<grid, TREES_PER_CTA * 8, 0, st>>>(p);
+    else if (e->L == 16 && e->PW == 1) k_step_continuous<16, 1, BK, SEL><<<grid, TREES_PER_CTA * 16, 0, st>>>(p);
+    else if (e->L == 16 && e->PW == 2) k_step_continuous<16, 2, BK, SEL><<<grid, TREES_PER_CTA * 16, 0, st>>>(p);
+    else if (e->L == 16 && e->PW == 4) k_step_continuous<16, 4, BK, SEL><<<grid, TREES_PER_CTA * 16, 0, st>>>(p);
+    else if (e->L == 32 && e->PW == 1) k_step_continuous<32, 1, BK, SEL><<<grid, TREES_PER_CTA * 32, 0, st>>>(p);
+    else if (e->L == 32 && e->PW == 2) k_step_continuous<32, 2, BK, SEL><<<grid, TREES_PER_CTA * 32, 0, st>>>(p);
+    else k_step_continuous<32, 4, BK, SEL><<<grid, TREES_PER_CTA * 32, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// enqueue the whole search on `st`; returns the number of kernels launched
+static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStream_t st, cudaError_t* cerr) {
+    const TreeParams p = make_params(e, B, tree_id0);
+    const MlpParams m = make_mlp_params(e, B);
+    const bool tape = p.use_tape != 0;
+    int launches = 0;
+    cudaError_t ce = cudaSuccess;
+#define LK(expr)                              \
+    do {                                      \
+        expr;                                 \
+        ++launches;                           \
+        if (ce == cudaSuccess) ce = cudaGetLastError(); \
+    } while (0)
+    const int tb = 128, tg = (B + tb - 1) / tb;
+    if (e->cfg.variant == AZG_DISCRETE) {
+        LK((k_init_discrete<<<tg, tb, 0, st>>>(p)));
+        if (!tape) LK(ce = launch_mlp(e, m, st));
+        for (int it = 0; it < N; ++it) {
+            if (it == 0) LK((k_step_discrete<false, true><<<tg, tb, 0, st>>>(p)));
+            else LK((k_step_discrete<true, true><<<tg, tb, 0, st>>>(p)));
+            if (!tape) LK(ce = launch_mlp(e, m, st));
+        }
+        LK((k_step_discrete<true, false><<<tg, tb, 0, st>>>(p)));
+    } else {
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(e->cparent, 0xFF, (size_t)B * e->PSTRIDE, st);
+        LK((k_init_continuous<<<tg, tb, 0, st>>>(p)));
+        if (!tape) LK(ce = launch_mlp(e, m, st));
+        LK((k_root_insert_continuous<<<tg, tb, 0, st>>>(p)));
+        for (int it = 0; it < N; ++it) {
+            if (it == 0) LK(ce = (launch_step_continuous<false, true>(e, p, st)));
+            else LK(ce = (launch_step_continuous<true, true>(e, p, st)));
+            if (!tape) LK(ce = launch_mlp(e, m, st));
+        }
+        LK(ce = (launch_step_continuous<true, false>(e, p, st)));
+    }
+#undef LK
+    *cerr = ce;
+    return launches;
+}
+
+static int run_search(azg_engine* e, int B, const double* d_root_state, const int32_t* d_root_n_init, int N, int64_t tree_id0,
+                      cudaStream_t st) {
+    if (!e) return fail(AZG_EINVAL, "null engine");
+    if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range (max_trees = " + std::to_string(e->cfg.max_trees) + ")");
+    if (N < 1 || N > e->cfg.max_rollouts) return fail(AZG_EINVAL, "n_rollouts out of range (max_rollouts = " + std::to_string(e->cfg.max_rollouts) + ")");
+    if (!d_root_state) return fail(AZG_EINVAL, "null root state");
+    if (!e->weights_set && !e->tapeV) return fail(AZG_EINVAL, "azg_set_weights has not been called");
+    CK(cudaSetDevice(e->cfg.device));
+    const int sd = e->cfg.variant == AZG_DISCRETE ? 4 : 2;
+    // stage the roots in engine-owned buffers so the captured graph has fixed addresses
+    if (d_root_state != e->root_state)
+        CK(cudaMemcpyAsync(e->root_state, d_root_state, (size_t)B * sd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (e->cfg.variant == AZG_DISCRETE) {
+        if (d_root_n_init) {
+            if (d_root_n_init != e->root_n_init)
+                CK(cudaMemcpyAsync(e->root_n_init, d_root_n_init, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        } else {
+            CK(cudaMemsetAsync(e->root_n_init, 0, (size_t)B * sizeof(int32_t), st));
+        }
+    }
+    cudaError_t ce = cudaSuccess;
+    if (e->cfg.flags & AZG_FLAG_NO_GRAPH) {
+        e->launches = enqueue_search(e, B, N, tree_id0, st, &ce);
+        if (ce != cudaSuccess) return fail(AZG_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(ce));
+    } else {
+        const int tape = e->tapeV != nullptr;
+        const auto key = std::make_tuple(B, N, tape, tree_id0, 0);
+        auto it = e->graphs.find(key);
+        if (it == e->graphs.end() || tape) {  // tape pointers may change between calls: always re-capture
+            if (it != e->graphs.end()) {
+                cudaGraphExecDestroy(it->second);
+                e->graphs.erase(it);
+            }
+            cudaGraph_t g = nullptr;
+            CK(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
+            const int n = enqueue_search(e, B, N, tree_id0, e->own_stream, &ce);
+            cudaError_t ee = cudaStreamEndCapture(e->own_stream, &g);
+            if (ce != cudaSuccess || ee != cudaSuccess) {
+                if (g) cudaGraphDestroy(g);
+                return fail(AZG_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ce != cudaSuccess ? ce : ee));
+            }
+            cudaGraphExec_t ge = nullptr;
+            cudaError_t ie = cudaGraphInstantiate(&ge, g, 0);
+            cudaGraphDestroy(g);
+            if (ie != cudaSuccess) return fail(AZG_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(ie));
+            if (e->graphs.size() > 32) {
+                for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
+                e->graphs.clear();
+            }
+            e->graphs[key] = ge;
+            e->launches = n;
+            it = e->graphs.find(key);
+        }
+        e->launches = 2 * (int64_t)N + 3 + (e->cfg.variant == AZG_CONTINUOUS ? 1 : 0) - (tape ? N + 1 : 0);
+        CK(cudaGraphLaunch(it->second, st));
+    }
+    e->last_B = B;
+    e->last_N = N;
+    return AZG_OK;
+}
+
+extern "C" int azg_search_discrete(azg_engine* e, int32_t B, const double* d_root_state, const int32_t* d_root_n_init,
+                                   int32_t n_rollouts, int64_t tree_id0, void* stream) {
+    if (e && e->cfg.variant != AZG_DISCRETE) return fail(AZG_EINVAL, "engine was created for the continuous variant");
+    return run_search(e, B, d_root_state, d_root_n_init, n_rollouts, tree_id0, (cudaStream_t)stream);
+}
+
+extern "C" int azg_search_continuous(azg_engine* e, int32_t B, const double* d_root_state, int32_t n_rollouts, int64_t tree_id0,
+                                     void* stream) {
+    if (e && e->cfg.variant != AZG_CONTINUOUS) return fail(AZG_EINVAL, "engine was created for the discrete variant");
+    return run_search(e, B, d_root_state, nullptr, n_rollouts, tree_id0, (cudaStream_t)stream);
+}
+
+extern "C" int azg_root_results(azg_engine* e, int32_t B, float* d_actions, int32_t* d_counts, double* d_Q, double* d_V_target,
+                                int32_t* d_n_children, void* stream) {
+    if (!e || !d_actions || !d_counts || !d_Q || !d_V_target || !d_n_children) return fail(AZG_EINVAL, "null argument");
+    if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
+    CK(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const TreeParams p = make_params(e, B, 0);
+    const int tb = 128, tg = (B + tb - 1) / tb;
+    if (e->cfg.variant == AZG_DISCRETE) k_results_discrete<<<tg, tb, 0, st>>>(p, e->cmax, d_actions, d_counts, d_Q, d_V_target, d_n_children);
+    else k_results_continuous<<<tg, tb, 0, st>>>(p, e->cmax, d_actions, d_counts, d_Q, d_V_target, d_n_children);
+    CK(cudaGetLastError());
+    return AZG_OK;
+}
+
+extern "C" int azg_status(azg_engine* e, void* stream) {
+    if (!e) return fail(AZG_EINVAL, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    int32_t h = 0;
+    CK(cudaMemcpyAsync(&h, e->err, sizeof h, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    if (h) CK(cudaMemsetAsync(e->err, 0, sizeof h, (cudaStream_t)stream));
+    if (h & ERR_NAN) return fail(AZG_ENAN, "NaN in a UCT vector (helpers.py:47-48)");
+    if (h & ERR_CAPACITY) return fail(AZG_ECAPACITY, "tree arena or child fan-out capacity exceeded");
+    return AZG_OK;
+}
+
+extern "C" int azg_search_host(azg_engine* e, int32_t B, const double* h_root_state, const int32_t* h_root_n_init, int32_t n_rollouts,
+                               int64_t tree_id0, float* h_actions, int32_t* h_counts, double* h_Q, double* h_V_target,
+                               int32_t* h_n_children) {
+    if (!e || !h_root_state || !h_actions || !h_counts || !h_Q || !h_V_target || !h_n_children) return fail(AZG_EINVAL, "null argument");
+    if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
+    if (e->cfg.variant == AZG_CONTINUOUS && h_root_n_init) return fail(AZG_EINVAL, "root_n_init is a discrete-only argument");
+    CK(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = e->own_stream;
+    const int sd = e->cfg.variant == AZG_DISCRETE ? 4 : 2;
+    const size_t cm = e->cmax;
+    // carve the pinned staging buffer
+    char* hp = (char*)e->h_pinned;
+    double* p_root = (double*)hp; hp += (size_t)B * 4 * sizeof(double);
+    double* p_Q = (double*)hp; hp += (size_t)B * cm * sizeof(double);
+    double* p_Vt = (double*)hp; hp += (size_t)B * sizeof(double);
+    float* p_act = (float*)hp; hp += (size_t)B * cm * sizeof(float);
+    int32_t* p_cnt = (int32_t*)hp; hp += (size_t)B * cm * sizeof(int32_t);
+    int32_t* p_nc = (int32_t*)hp; hp += (size_t)B * sizeof(int32_t);
+    int32_t* p_rn = (int32_t*)hp;
+    memcpy(p_root, h_root_state, (size_t)B * sd * sizeof(double));
+    CK(cudaMemcpyAsync(e->root_state, p_root, (size_t)B * sd * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int32_t* d_rn = nullptr;
+    if (h_root_n_init) {
+        memcpy(p_rn, h_root_n_init, (size_t)B * sizeof(int32_t));
+        CK(cudaMemcpyAsync(e->root_n_init, p_rn, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        d_rn = e->root_n_init;
+    }
+    int rc = run_search(e, B, e->root_state, d_rn, n_rollouts, tree_id0, st);
+    if (rc) return rc;
+    rc = azg_root_results(e, B, e->r_actions, e->r_counts, e->r_Q, e->r_Vt, e->r_nchild, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(p_act, e->r_actions, (size_t)B * cm * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p_cnt, e->r_counts, (size_t)B * cm * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p_Q, e->r_Q, (size_t)B * cm * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p_Vt, e->r_Vt, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(p_nc, e->r_nchild, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    rc = azg_status(e, st);  // synchronises
+    memcpy(h_actions, p_act, (size_t)B * cm * sizeof(float));
+    memcpy(h_counts, p_cnt, (size_t)B * cm * sizeof(int32_t));
+    memcpy(h_Q, p_Q, (size_t)B * cm * sizeof(double));
+    memcpy(h_V_target, p_Vt, (size_t)B * sizeof(double));
+    memcpy(h_n_children, p_nc, (size_t)B * sizeof(int32_t));
+    return rc;
+}
+
+extern "C" int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]) {
+    if (!e || !out) return fail(AZG_EINVAL, "null argument");
+    if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    std::vector<uint32_t> c(4 * (size_t)B);
+    std::vector<int32_t> dr(B), pw(B);
+    // counters are laid out [4][B_of_the_search]; the search that wrote them used last_B
+    const int LB = e->last_B > 0 ? e->last_B : B;
+    std::vector<uint32_t> all(4 * (size_t)LB);
+    CK(cudaMemcpy(all.data(), e->ctr, all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dr.data(), e->draws, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(pw.data(), e->pw, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; ++k) out[k] = 0;
+    const int nb = std::min(B, LB);
+    for (int t = 0; t < nb; ++t) {
+        out[1] += all[t];
+        out[2] += all[(size_t)LB + t];
+        out[6] += all[(size_t)2 * LB + t];
+        out[4] += all[(size_t)3 * LB + t];
+        out[5] += dr[t];
+        out[3] += pw[t];
+    }
+    out[0] = (int64_t)nb * e->last_N;
+    out[7] = e->launches;
+    return AZG_OK;
+}
+
+// ---- tree dump (host side unpacking of the device tables) ------------------------------------------------
+extern "C" int azg_dump_tree_discrete(azg_engine* e, int32_t B, const azg_dump_discrete* o) {
+    if (!e || !o) return fail(AZG_EINVAL, "null argument");
+    if (e->cfg.variant != AZG_DISCRETE) return fail(AZG_EINVAL, "engine is not discrete");
+    if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    const size_t R = e->R, A = 2;
+    std::vector<DRow> rows((size_t)B * R);
+    std::vector<double> st((size_t)B * R * 4);
+    std::vector<int32_t> nr(B);
+    CK(cudaMemcpy(rows.data(), e->drows, rows.size() * sizeof(DRow), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(st.data(), e->dstate, st.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nr.data(), e->n_rows, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < (size_t)B; ++t) {
+        o->n_nodes[t] = nr[t];
+        for (size_t i = 0; i < R; ++i) {
+            const size_t q = t * R + i;
+            const bool live = (int)i < nr[t];
+            const DRow& r = rows[q];
+            o->parent[q] = live ? (r.parent == DROW_NONE ? -1 : r.parent) : 0;
+            o->paction[q] = live ? (r.parent == DROW_NONE ? -1 : r.paction) : 0;
+            o->node_n[q] = live ? r.node_n : 0;
+            o->terminal[q] = live ? (r.flags & ROW_TERMINAL) : 0;
+            o->V[q] = live ? r.V : 0.0f;
+            o->r[q] = live ? r.r : 0.0;
+            for (size_t k = 0; k < 4; ++k) o->state[q * 4 + k] = live ? st[q * 4 + k] : 0.0;
+            for (size_t a = 0; a < A; ++a) {
+                o->prior[q * A + a] = live ? r.prior[a] : 0.0f;
+                o->eW[q * A + a] = live ? r.W[a] : 0.0;
+                o->en[q * A + a] = live ? r.n_e[a] : 0;
+                o->echild[q * A + a] = live ? (r.child[a] == DROW_NONE ? -1 : r.child[a]) : 0;
+            }
+        }
+    }
+    return AZG_OK;
+}
+
+extern "C" int azg_dump_tree_continuous(azg_engine* e, int32_t B, const azg_dump_continuous* o) {
+    if (!e || !o) return fail(AZG_EINVAL, "null argument");
+    if (e->cfg.variant != AZG_CONTINUOUS) return fail(AZG_EINVAL, "engine is not continuous");
+    if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    const size_t R = e->R, K3 = e->K3, HS = e->HS, PS = e->PSTRIDE;
+    std::vector<CRow> rows((size_t)B * R);
+    std::vector<double2> st((size_t)B * R);
+    std::vector<float> hd((size_t)B * R * HS);
+    std::vector<uint8_t> par((size_t)B * PS);
+    std::vector<int32_t> nr(B);
+    CK(cudaMemcpy(rows.data(), e->crows, rows.size() * sizeof(CRow), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(st.data(), e->cstate, st.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(hd.data(), e->chead, hd.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(par.data(), e->cparent, par.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nr.data(), e->n_rows, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (size_t t = 0; t < (size_t)B; ++t) {
+        o->n_rows[t] = nr[t];
+        for (size_t i = 0; i < R; ++i) {
+            const size_t q = t * R + i;
+            const bool live = (int)i < nr[t];
+            const CRow& r = rows[q];
+            const bool ex = live && (r.nn_flags & CROW_EXPANDED);
+            o->parent[q] = live ? (i == 0 ? -1 : par[t * PS + i]) : 0;
+            o->action[q] = live && i > 0 ? r.action : 0.0f;
+            o->eW[q] = live ? r.W : 0.0;
+            o->en[q] = live ? r.n_e : 0;
+            o->expanded[q] = ex ? 1 : 0;
+            o->node_n[q] = ex ? (int32_t)(r.nn_flags & CROW_NMASK) : 0;
+            o->terminal[q] = ex && (r.nn_flags & CROW_TERMINAL) ? 1 : 0;
+            o->V[q] = ex ? r.V : 0.0f;
+            o->r[q] = ex ? r.r : 0.0;
+            o->state[q * 2] = ex ? st[q].x : 0.0;
+            o->state[q * 2 + 1] = ex ? st[q].y : 0.0;
+            for (size_t k = 0; k < K3; ++k) o->head[q * K3 + k] = ex ? hd[q * HS + k] : 0.0f;
+        }
+    }
+    return AZG_OK;
+}
+
+// ---- standalone building blocks for known-answer tests --------------------------------------------------
+extern "C" int azg_mlp_forward(azg_engine* e, int32_t n, const float* d_x, float* d_V, float* d_head, void* stream) {
+    if (!e || !d_x || !d_V || !d_head) return fail(AZG_EINVAL, "null argument");
+    if (n < 1) return fail(AZG_EINVAL, "n must be >= 1");
+    if (!e->weights_set) return fail(AZG_EINVAL, "azg_set_weights has not been called");
+    CK(cudaSetDevice(e->cfg.device));
+    MlpParams m = make_mlp_params(e, n);
+    m.X = d_x; m.xstride = e->cfg.state_dim; m.mode = 1; m.outV = d_V; m.outHead = d_head; m.evals = nullptr;
+    CK(launch_mlp(e, m, (cudaStream_t)stream));
+    return AZG_OK;
+}
+
+__global__ void k_env_step(int variant, int n, const double* s, const float* a, double* o, double* rew, int32_t* term, float* obs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (variant == AZG_DISCRETE) {
+        const double in[4] = {s[i * 4], s[i * 4 + 1], s[i * 4 + 2], s[i * 4 + 3]};
+        double out[4], r;
+        const bool t = env::cartpole_step(in, (int)a[i], out, r);
+        for (int k = 0; k < 4; ++k) { o[i * 4 + k] = out[k]; obs[i * 4 + k] = (float)out[k]; }
+        rew[i] = r;
+        term[i] = t;
+    } else {
+        double nth, nthdot, r;
+        const bool t = env::pendulum_step(s[i * 2], s[i * 2 + 1], a[i], nth, nthdot, r);
+        o[i * 2] = nth; o[i * 2 + 1] = nthdot;
+        const float4 ob = env::pendulum_obs(nth, nthdot);
+        obs[i * 3] = ob.x; obs[i * 3 + 1] = ob.y; obs[i * 3 + 2] = ob.z;
+        rew[i] = r;
+        term[i] = t;
+    }
+}
+
+extern "C" int azg_env_step(azg_engine* e, int32_t n, const double* d_state, const float* d_action, double* d_next, double* d_reward,
+                            int32_t* d_terminal, float* d_obs, void* stream) {
+    if (!e || !d_state || !d_action || !d_next || !d_reward || !d_terminal || !d_obs) return fail(AZG_EINVAL, "null argument");
+    if (n < 1) return fail(AZG_EINVAL, "n must be >= 1");
+    CK(cudaSetDevice(e->cfg.device));
+    k_env_step<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(e->cfg.variant, n, d_state, d_action, d_next, d_reward, d_terminal, d_obs);
+    CK(cudaGetLastError());
+    return AZG_OK;
+}

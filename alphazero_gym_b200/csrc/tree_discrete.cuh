@@ -1,0 +1,191 @@
+// tree_discrete.cuh -- backup + PUCT select + expansion for the discrete (CartPole) tree.
+//
+// Reference: MCTSDiscrete.search (mcts.py:418-462), selectionUCT (:464-493), epsilon_greedy (:175-195),
+// helpers.argmax (helpers.py:30-52), MCTS.backprop (mcts.py:241-267), Action.update (states.py:97-112),
+// expansion (mcts.py:215-238).
+//
+// Mapping: fan-out is A = 2, so a warp-wide argmax would idle 30 lanes; instead one THREAD owns one tree
+// and a warp advances 32 trees in lockstep.  A node visit is one 64 B row = two full 32 B sectors, read
+// with 4 x LDG.128; the level loop is a chain of dependent row loads (parent -> chosen child).  The env
+// step runs after the loop so that all 32 lanes execute the f64 dynamics together.
+#pragma once
+#include "common.cuh"
+#include "env.cuh"
+
+__device__ __forceinline__ DRow load_drow(const DRow* p) {
+    DRow r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+    return r;
+}
+
+// root row + first network input (MCTSDiscrete.initialize_search, mcts.py:364-383)
+__global__ void k_init_discrete(const TreeParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.B) return;
+    const double* s = p.root_state + (size_t)t * 4;
+    double* st = p.dstate + (size_t)t * p.R * 4;
+    DRow row;
+    row.W[0] = row.W[1] = 0.0;
+    row.r = 0.0;
+    row.n_e[0] = row.n_e[1] = 0;
+    row.prior[0] = row.prior[1] = 0.0f;
+    row.V = 0.0f;
+    row.node_n = p.root_n_init ? p.root_n_init[t] : 0;
+    row.child[0] = row.child[1] = DROW_NONE;
+    row.parent = DROW_NONE;
+    row.paction = 0;
+    row.flags = 0;
+    row.pad[0] = row.pad[1] = 0;
+    if (p.use_tape) {
+        row.V = p.tapeV[(size_t)t * p.R];
+        row.prior[0] = p.tapeP[(size_t)t * p.R * 2];
+        row.prior[1] = p.tapeP[(size_t)t * p.R * 2 + 1];
+    }
+    p.drows[(size_t)t * p.R] = row;
+    st[0] = s[0]; st[1] = s[1]; st[2] = s[2]; st[3] = s[3];
+    p.X[t] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
+    p.leaf[t] = 0 | LEAF_EVAL;
+    p.n_rows[t] = 1;
+    p.draws[t] = 0;
+    p.pw[t] = 0;
+    p.depth[t] = 0;
+    for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
+}
+
+template <bool BACKUP, bool SELECT>
+__global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.B) return;
+    DRow* rows = p.drows + (size_t)t * p.R;
+
+    if (BACKUP) {
+        // R = leaf.V; up the path: R = node.r + gamma*R; edge.n += 1; edge.W += R; parent.n += 1
+        const int leaf = p.leaf[t] & LEAF_ROW_MASK;
+        const DRow lr = load_drow(rows + leaf);
+        double Rv = (double)lr.V;
+        double r = lr.r;
+        int parent = lr.parent, pa = lr.paction;
+        while (parent != DROW_NONE) {
+            Rv = r + p.gamma * Rv;
+            DRow* pr = rows + parent;
+            const DRow prow = load_drow(pr);
+            pr->W[pa] = prow.W[pa] + Rv;
+            pr->n_e[pa] = prow.n_e[pa] + 1;
+            pr->node_n = prow.node_n + 1;
+            r = prow.r;
+            pa = prow.paction;
+            parent = prow.parent;
+        }
+    }
+
+    if (SELECT) {
+        const int64_t tree = p.tree_id0 + t;
+        int draws = p.draws[t];
+        int cur = 0;
+        DRow row = load_drow(rows);
+        int a = -1;
+        uint32_t levels = 0;
+        bool nan = false;
+        while (true) {
+            // UCT_a = Q_a + prior_a*c_uct*(sqrt(node.n+1)/(n_a+1))   (mcts.py:483-484)
+            const double sq = sqrt((double)(row.node_n + 1));
+            double u[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int n = row.n_e[i];
+                const double Q = n > 0 ? row.W[i] / (double)n : (double)row.V;
+                const double pc = p.puct_f32 ? (double)__fmul_rn(row.prior[i], (float)p.c_uct) : (double)row.prior[i] * p.c_uct;
+                u[i] = Q + pc * (sq / (double)(n + 1));
+            }
+            nan |= (u[0] != u[0]) || (u[1] != u[1]);
+            bool random_pick = false;
+            if (p.epsilon != 0) {  // epsilon_greedy: random.random() < eps -> random.randint(0, A-1)
+                const double x = (double)u32_to_unit(rng_select_u32(p, tree, draws++));
+                random_pick = x < p.epsilon;
+            }
+            if (random_pick) {
+                a = u32_to_index(rng_select_u32(p, tree, draws++), 2);
+            } else {
+                // argmax with random tie-break: one draw is consumed even for a single winner
+                if (u[0] == u[1]) a = u32_to_index(rng_select_u32(p, tree, draws), 2);
+                else a = u[1] > u[0] ? 1 : 0;
+                ++draws;
+            }
+            ++levels;
+            const int child = row.child[a];
+            if (child == DROW_NONE) break;  // expansion
+            cur = child;
+            row = load_drow(rows + cur);
+            if (row.flags & ROW_TERMINAL) { a = -1; break; }  // trace ends on an existing terminal node
+        }
+        if (nan) atomicOr(p.err, ERR_NAN);
+        p.draws[t] = draws;
+        p.ctr[t] += levels;
+        p.ctr[(size_t)p.B + t] += levels * 2;
+        if (a >= 0) {
+            const int child = p.n_rows[t];
+            if (child >= p.R) { atomicOr(p.err, ERR_CAPACITY); p.leaf[t] = cur; return; }
+            p.n_rows[t] = child + 1;
+            double* st = p.dstate + ((size_t)t * p.R + cur) * 4;
+            const double s[4] = {st[0], st[1], st[2], st[3]};
+            double o[4], rew;
+            const bool term = env::cartpole_step(s, a, o, rew);
+            double* so = p.dstate + ((size_t)t * p.R + child) * 4;
+            so[0] = o[0]; so[1] = o[1]; so[2] = o[2]; so[3] = o[3];
+            DRow nr;
+            nr.W[0] = nr.W[1] = 0.0;
+            nr.r = rew;
+            nr.n_e[0] = nr.n_e[1] = 0;
+            nr.prior[0] = nr.prior[1] = 0.0f;
+            nr.V = 0.0f;
+            nr.node_n = 0;
+            nr.child[0] = nr.child[1] = DROW_NONE;
+            nr.parent = (uint16_t)cur;
+            nr.paction = (uint8_t)a;
+            nr.flags = term ? ROW_TERMINAL : 0;
+            nr.pad[0] = nr.pad[1] = 0;
+            if (p.use_tape) {
+                const size_t ti = (size_t)t * p.R + child;
+                nr.V = term ? 0.0f : p.tapeV[ti];
+                nr.prior[0] = p.tapeP[ti * 2];
+                nr.prior[1] = p.tapeP[ti * 2 + 1];
+            }
+            rows[child] = nr;
+            rows[cur].child[a] = (uint16_t)child;
+            p.X[t] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+            p.leaf[t] = child | LEAF_EVAL | (term ? LEAF_TERMINAL : 0);
+        } else {
+            p.leaf[t] = cur;
+            p.ctr[(size_t)2 * p.B + t] += 1;
+        }
+    }
+}
+
+// MCTS.return_results (mcts.py:269-307) for the discrete root
+__global__ void k_results_discrete(const TreeParams p, int cmax, float* actions, int32_t* counts, double* Q, double* Vt,
+                                   int32_t* nchild) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.B) return;
+    const DRow row = load_drow(p.drows + (size_t)t * p.R);
+    double q[2];
+    for (int a = 0; a < 2; ++a) {
+        const int n = row.n_e[a];
+        q[a] = n > 0 ? row.W[a] / (double)n : (double)row.V;
+        actions[(size_t)t * cmax + a] = (float)a;
+        counts[(size_t)t * cmax + a] = n;
+        Q[(size_t)t * cmax + a] = q[a];
+    }
+    nchild[t] = 2;
+    double v;
+    if (p.v_target == 1) {  // on_policy: np.sum((counts / np.sum(counts)) * Q), n < 8 -> sequential sum from 0.
+        const double tot = (double)(row.n_e[0] + row.n_e[1]);
+        v = 0.0;
+        v += ((double)row.n_e[0] / tot) * q[0];
+        v += ((double)row.n_e[1] / tot) * q[1];
+    } else {
+        v = q[1] > q[0] ? q[1] : q[0];
+    }
+    Vt[t] = v;
+}

@@ -1,0 +1,167 @@
+/*
+ * azg.h -- C ABI of the B200-native batched MCTS engine (libazg.so).
+ *
+ * This is the drop-in boundary for the search hot path of timoklein/alphazero-gym.  The reference has
+ * no FFI: its seam is the Python class chosen by Hydra `_target_` (config/mcts/MCTSDiscrete.yaml:2,
+ * config/mcts/MCTSContinuous.yaml:2) and built by the agent (alphazero/agent/agents.py:82).  The host
+ * side (alphazero_gym_b200/search/mcts.py) keeps that class interface and calls these entry points
+ * through ctypes with raw pointers -- no torch types cross this boundary.  INTEGRATION.md shows the
+ * binding a reference maintainer would add.
+ *
+ * Conventions: every function returns 0 on success and a negative AZG_E* code on failure, with a
+ * message available from azg_last_error() (thread-local).  No exceptions cross the boundary.  One engine
+ * per GPU; calls on one handle are stream-ordered and not thread-safe.  `stream` is a cudaStream_t
+ * passed as void* (NULL = the legacy default stream).  Pointers named d_* are device pointers owned by
+ * the caller, h_* are host pointers.  There is no CPU fallback: without a CUDA device azg_create fails.
+ */
+#ifndef AZG_H
+#define AZG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZG_OK 0
+#define AZG_EINVAL -1      /* bad argument / unsupported configuration */
+#define AZG_ECUDA -2       /* CUDA runtime error (message has the cudaError string) */
+#define AZG_ETERMINAL -3   /* "Can't do tree search from a terminal node" (mcts.py:382-383, :599-600) */
+#define AZG_ENAN -4        /* NaN met in a UCT vector (helpers.py:47-48 only warns; we refuse) */
+#define AZG_ECAPACITY -5   /* tree arena / child fan-out capacity exceeded */
+
+#define AZG_DISCRETE 0   /* MCTSDiscrete  + CartPole-v0 dynamics + DiscretePolicy   */
+#define AZG_CONTINUOUS 1 /* MCTSContinuous + Pendulum-v0 dynamics + DiagonalNormal/GMM policy */
+
+#define AZG_ACT_RELU 0
+#define AZG_ACT_ELU 1
+
+#define AZG_VT_OFF_POLICY 0 /* mcts.py:131 */
+#define AZG_VT_ON_POLICY 1  /* mcts.py:111 */
+#define AZG_VT_GREEDY 2     /* mcts.py:133-173 */
+
+/* Constructor arguments of the reference classes (mcts.py:316-327 MCTSDiscrete, :537-549
+ * MCTSContinuous) plus what `model` implies (policies.py:806 make_policy) and engine capacity. */
+typedef struct azg_config {
+    int32_t variant;        /* AZG_DISCRETE | AZG_CONTINUOUS */
+    int32_t max_rollouts;   /* capacity: largest n_rollouts a search call may ask for */
+    int32_t max_trees;      /* capacity: largest batch B */
+    int32_t num_actions;    /* discrete: 2 (CartPole) */
+    int32_t num_components; /* continuous: K mixture components (1 = DiagonalNormalPolicy) */
+    int32_t state_dim;      /* network input width: 4 CartPole, 3 Pendulum */
+    int32_t hidden;         /* hidden width (all hidden layers equal; 128 in both shipped configs) */
+    int32_t n_hidden;       /* hidden layers: 2 (DiscretePolicy.yaml) / 3 (ContinuousPolicy.yaml) */
+    int32_t activation;     /* AZG_ACT_* */
+    int32_t v_target;       /* AZG_VT_* (V_target_policy) */
+    int32_t puct_f32;       /* 1: prior*c_uct rounded to f32 as numpy>=2 does (mcts.py:484); 0: f64 */
+    int32_t device;         /* CUDA device ordinal */
+    double c_uct, gamma, epsilon, c_pw, kappa;
+    float action_bound, log_std_min, log_std_max;
+    uint32_t flags;         /* AZG_FLAG_* */
+    uint64_t seed;          /* Philox key for tie-break / eps-greedy / action-noise streams */
+} azg_config;
+
+#define AZG_FLAG_NO_GRAPH 1u /* launch kernels directly instead of replaying a captured CUDA graph */
+
+typedef struct azg_engine azg_engine;
+
+int azg_create(const azg_config* cfg, azg_engine** out);
+void azg_destroy(azg_engine* e);
+const char* azg_last_error(void);
+const char* azg_version(void);
+
+/* Network weights: flat f32 in state_dict order -- trunk.{0,2,..}.{weight,bias}, value_head.{weight,bias},
+ * dist_head.{weight,bias} (policies.py:101-120, :255-259, :434, :588).  `flat` may be a host or a device
+ * pointer (detected).  Replaces the per-node model.predict_V / predict_pi / sample_action callbacks
+ * (mcts.py:406-416, :619-623, :652). */
+int64_t azg_num_weights(const azg_engine* e);
+int azg_set_weights(azg_engine* e, const float* flat, int64_t n, void* stream);
+
+/* Batched MCTSDiscrete.search (mcts.py:418-462) over B CartPole roots.
+ * d_root_state [B][4] f64 hidden env state (x, x_dot, theta, theta_dot);
+ * d_root_n_init [B] carried-over root visit count after forward() (mcts.py:495-526) or NULL;
+ * tree_id0: global id of tree 0 -- tree i's RNG streams are keyed by tree_id0+i, which makes results
+ * independent of batch composition and of how trees are sharded over GPUs. */
+int azg_search_discrete(azg_engine* e, int32_t B, const double* d_root_state, const int32_t* d_root_n_init,
+                        int32_t n_rollouts, int64_t tree_id0, void* stream);
+
+/* Batched MCTSContinuous.search (mcts.py:656-702) over B Pendulum roots; d_root_state [B][2] (th, thdot). */
+int azg_search_continuous(azg_engine* e, int32_t B, const double* d_root_state, int32_t n_rollouts, int64_t tree_id0,
+                          void* stream);
+
+/* MCTS.return_results (mcts.py:269-307) for the last search: per tree, root children in insertion order.
+ * Row stride is azg_cmax(e).  actions: action index (discrete) or sampled action (continuous). */
+int32_t azg_cmax(const azg_engine* e);
+int azg_root_results(azg_engine* e, int32_t B, float* d_actions, int32_t* d_counts, double* d_Q, double* d_V_target,
+                     int32_t* d_n_children, void* stream);
+
+/* Host-buffer convenience = what MCTS*.search + return_results cost end to end: H2D of the roots,
+ * search, result extraction, D2H of the results, synchronised on return.  h_root_n_init may be NULL
+ * (and must be for the continuous variant). */
+int azg_search_host(azg_engine* e, int32_t B, const double* h_root_state, const int32_t* h_root_n_init, int32_t n_rollouts,
+                    int64_t tree_id0, float* h_actions, int32_t* h_counts, double* h_Q, double* h_V_target,
+                    int32_t* h_n_children);
+
+/* Device status of the last search(es): AZG_OK, AZG_ENAN or AZG_ECAPACITY.  Synchronises `stream`. */
+int azg_status(azg_engine* e, void* stream);
+
+/* ---- parity hooks: evaluator injection and full tree dump -------------------------------- */
+/* Tapes are device arrays indexed by tree and by node/row creation index, stride azg_rows(e):
+ * V [B][R]; prior [B][R][A] (discrete); action [B][R] (continuous).  Passing d_V = NULL returns to the
+ * engine's own MLP + noise.  With tapes set no network kernel runs. */
+int32_t azg_rows(const azg_engine* e); /* = max_rollouts + 2 */
+int azg_set_tapes(azg_engine* e, const float* d_V, const float* d_prior, const float* d_action);
+
+typedef struct azg_dump_discrete { /* host arrays, R = azg_rows(e), A = num_actions; nodes in creation order */
+    int32_t* n_nodes;  /* [B] */
+    int32_t* parent;   /* [B][R] (-1 root) */
+    int32_t* paction;  /* [B][R] */
+    int32_t* node_n;   /* [B][R] Node.n */
+    int32_t* terminal; /* [B][R] */
+    float* V;          /* [B][R] */
+    double* r;         /* [B][R] */
+    double* state;     /* [B][R][4] */
+    float* prior;      /* [B][R][A] */
+    double* eW;        /* [B][R][A] Action.W */
+    int32_t* en;       /* [B][R][A] Action.n */
+    int32_t* echild;   /* [B][R][A] (-1 none) */
+} azg_dump_discrete;
+
+typedef struct azg_dump_continuous { /* host arrays; rows in creation order, row 0 = root */
+    int32_t* n_rows;   /* [B] */
+    int32_t* parent;   /* [B][R] (-1 root) */
+    float* action;     /* [B][R] */
+    double* eW;        /* [B][R] */
+    int32_t* en;       /* [B][R] */
+    int32_t* expanded; /* [B][R] */
+    int32_t* node_n;   /* [B][R] */
+    int32_t* terminal; /* [B][R] */
+    float* V;          /* [B][R] */
+    double* r;         /* [B][R] */
+    double* state;     /* [B][R][2] */
+    float* head;       /* [B][R][3K] mu, sigma, mixture prob */
+} azg_dump_continuous;
+
+int azg_dump_tree_discrete(azg_engine* e, int32_t B, const azg_dump_discrete* out);
+int azg_dump_tree_continuous(azg_engine* e, int32_t B, const azg_dump_continuous* out);
+
+/* counters of the last search, summed over trees: [0] simulations, [1] selection levels, [2] child edges
+ * scanned, [3] progressive-widening inserts, [4] network evaluations, [5] RNG draws, [6] simulations that
+ * ended on a terminal node, [7] kernels launched (or graph nodes replayed). */
+int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]);
+
+/* Batched network forward on its own (known-answer tests of the evaluation kernel):
+ * d_x [n][state_dim] -> d_V [n], d_head [n][azg_head_dim(e)] post-processed head
+ * (discrete: softmax priors [A]; continuous: mu[K], sigma[K], prob[K]). */
+int32_t azg_head_dim(const azg_engine* e);
+int azg_mlp_forward(azg_engine* e, int32_t n, const float* d_x, float* d_V, float* d_head, void* stream);
+
+/* Batched env.step on its own (known-answer tests): d_state [n][4|2], d_action [n] (index as float for
+ * CartPole) -> d_next [n][4|2], d_reward [n] (raw env reward), d_terminal [n], d_obs [n][state_dim]. */
+int azg_env_step(azg_engine* e, int32_t n, const double* d_state, const float* d_action, double* d_next, double* d_reward,
+                 int32_t* d_terminal, float* d_obs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

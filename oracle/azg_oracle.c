@@ -531,7 +531,7 @@ static int search_discrete_one(const azo_config* c, const net_t* net, const azo_
     for (int i = 0; i < 4; ++i) t->state[i] = root_state[i];
     d_evaluate(c, net, tp, b, t, 0, ctr);
     for (int it = 0; it < c->n_rollouts; ++it) {
-        int node = 0;
+        int node = 0, created = 0;
         while (!t->terminal[node]) {
             double uct[AZO_MAX_A];
             double sq = sqrt((double)(t->node_n[node] + 1));
@@ -553,9 +553,10 @@ static int search_discrete_one(const azo_config* c, const net_t* net, const azo_
             t->echild[node * A + a] = child;
             d_evaluate(c, net, tp, b, t, child, ctr);
             node = child;
+            created = 1;
             break;
         }
-        if (t->terminal[node]) ctr[6]++;
+        if (!created) ctr[6]++; /* trace ended on an already existing terminal node */
         /* mcts.py:241-267 */
         double R = (double)t->V[node];
         while (t->parent[node] >= 0) {
@@ -646,7 +647,7 @@ static int search_continuous_one(const azo_config* c, const net_t* net, const az
     c_add_pw_action(c, tp, b, t, 0, g, ctr);
     const float g32 = (float)c->gamma;
     for (int it = 0; it < c->n_rollouts; ++it) {
-        int node = 0, depth = 0;
+        int node = 0, depth = 0, created = 0;
         while (!t->terminal[node]) {
             int kids[4096], C = 0;
             for (int i = 1; i < t->n_rows; ++i) if (t->parent[i] == node) kids[C++] = i;
@@ -674,9 +675,10 @@ static int search_continuous_one(const azo_config* c, const net_t* net, const az
             t->terminal[sel] = term; t->expanded[sel] = 1; t->node_n[sel] = 0;
             c_evaluate(c, net, tp, b, t, sel, ctr);
             node = sel;
+            created = 1;
             break;
         }
-        if (t->terminal[node]) ctr[6]++;
+        if (!created) ctr[6]++;
         /* backprop (mcts.py:241-267).  First step: gamma * (0-d f32 array) stays f32 under NEP 50. */
         double R = 0.0;
         for (int d = depth - 1; d >= 0; --d) {
