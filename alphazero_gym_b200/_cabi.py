@@ -21,7 +21,7 @@ EXPORTS = [
     "azg_create", "azg_destroy", "azg_last_error", "azg_version", "azg_num_weights", "azg_set_weights",
     "azg_search_discrete", "azg_search_continuous", "azg_cmax", "azg_root_results", "azg_search_host", "azg_status",
     "azg_rows", "azg_set_tapes", "azg_dump_tree_discrete", "azg_dump_tree_continuous", "azg_get_counters",
-    "azg_head_dim", "azg_mlp_forward", "azg_env_step",
+    "azg_head_dim", "azg_mlp_forward", "azg_env_step", "azg_profile_search",
 ]
 
 
@@ -84,6 +84,8 @@ def load():
     L.azg_dump_tree_discrete.restype, L.azg_dump_tree_discrete.argtypes = C.c_int, [vp, i32, C.POINTER(DumpDiscrete)]
     L.azg_dump_tree_continuous.restype, L.azg_dump_tree_continuous.argtypes = C.c_int, [vp, i32, C.POINTER(DumpContinuous)]
     L.azg_get_counters.restype, L.azg_get_counters.argtypes = C.c_int, [vp, i32, C.POINTER(i64 * 8)]
+    L.azg_profile_search.restype = C.c_int
+    L.azg_profile_search.argtypes = [vp, i32, vp, vp, i32, i64, vp, C.POINTER(C.c_float * 3), C.POINTER(i32 * 3)]
     L.azg_head_dim.restype, L.azg_head_dim.argtypes = i32, [vp]
     L.azg_mlp_forward.restype, L.azg_mlp_forward.argtypes = C.c_int, [vp, i32, vp, vp, vp, vp]
     L.azg_env_step.restype, L.azg_env_step.argtypes = C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp]

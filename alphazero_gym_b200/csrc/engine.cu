@@ -341,40 +341,61 @@ static cudaError_t launch_step_continuous(const azg_engine* e, const TreeParams&
     return cudaGetLastError();
 }
 
+// per-launch CUDA-event timing used by azg_profile_search (classes: 0 tree step, 1 evaluation, 2 setup)
+struct Prof {
+    std::vector<cudaEvent_t> ev;  // start/stop pairs
+    std::vector<int> cls;
+};
+
 // enqueue the whole search on `st`; returns the number of kernels launched
-static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStream_t st, cudaError_t* cerr) {
+static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStream_t st, cudaError_t* cerr, Prof* prof = nullptr) {
     const TreeParams p = make_params(e, B, tree_id0);
     const MlpParams m = make_mlp_params(e, B);
     const bool tape = p.use_tape != 0;
     int launches = 0;
     cudaError_t ce = cudaSuccess;
-#define LK(expr)                              \
-    do {                                      \
-        expr;                                 \
-        ++launches;                           \
+    auto begin = [&](int cls) {
+        if (!prof) return;
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        prof->ev.push_back(a);
+        prof->ev.push_back(b);
+        prof->cls.push_back(cls);
+        cudaEventRecord(a, st);
+    };
+    auto end = [&]() {
+        if (prof) cudaEventRecord(prof->ev.back(), st);
+    };
+#define LK(cls, expr)                                   \
+    do {                                                \
+        begin(cls);                                     \
+        expr;                                           \
+        end();                                          \
+        ++launches;                                     \
         if (ce == cudaSuccess) ce = cudaGetLastError(); \
     } while (0)
     const int tb = 128, tg = (B + tb - 1) / tb;
     if (e->cfg.variant == AZG_DISCRETE) {
-        LK((k_init_discrete<<<tg, tb, 0, st>>>(p)));
-        if (!tape) LK(ce = launch_mlp(e, m, st));
+        LK(2, (k_init_discrete<<<tg, tb, 0, st>>>(p)));
+        if (!tape) LK(1, ce = launch_mlp(e, m, st));
         for (int it = 0; it < N; ++it) {
-            if (it == 0) LK((k_step_discrete<false, true><<<tg, tb, 0, st>>>(p)));
-            else LK((k_step_discrete<true, true><<<tg, tb, 0, st>>>(p)));
-            if (!tape) LK(ce = launch_mlp(e, m, st));
+            if (it == 0) LK(0, (k_step_discrete<false, true><<<tg, tb, 0, st>>>(p)));
+            else LK(0, (k_step_discrete<true, true><<<tg, tb, 0, st>>>(p)));
+            if (!tape) LK(1, ce = launch_mlp(e, m, st));
         }
-        LK((k_step_discrete<true, false><<<tg, tb, 0, st>>>(p)));
+        LK(0, (k_step_discrete<true, false><<<tg, tb, 0, st>>>(p)));
     } else {
         if (ce == cudaSuccess) ce = cudaMemsetAsync(e->cparent, 0xFF, (size_t)B * e->PSTRIDE, st);
-        LK((k_init_continuous<<<tg, tb, 0, st>>>(p)));
-        if (!tape) LK(ce = launch_mlp(e, m, st));
-        LK((k_root_insert_continuous<<<tg, tb, 0, st>>>(p)));
+        LK(2, (k_init_continuous<<<tg, tb, 0, st>>>(p)));
+        if (!tape) LK(1, ce = launch_mlp(e, m, st));
+        LK(2, (k_root_insert_continuous<<<tg, tb, 0, st>>>(p)));
         for (int it = 0; it < N; ++it) {
-            if (it == 0) LK(ce = (launch_step_continuous<false, true>(e, p, st)));
-            else LK(ce = (launch_step_continuous<true, true>(e, p, st)));
-            if (!tape) LK(ce = launch_mlp(e, m, st));
+            if (it == 0) LK(0, ce = (launch_step_continuous<false, true>(e, p, st)));
+            else LK(0, ce = (launch_step_continuous<true, true>(e, p, st)));
+            if (!tape) LK(1, ce = launch_mlp(e, m, st));
         }
-        LK(ce = (launch_step_continuous<true, false>(e, p, st)));
+        LK(0, ce = (launch_step_continuous<true, false>(e, p, st)));
     }
 #undef LK
     *cerr = ce;
@@ -452,6 +473,41 @@ extern "C" int azg_search_continuous(azg_engine* e, int32_t B, const double* d_r
                                      void* stream) {
     if (e && e->cfg.variant != AZG_CONTINUOUS) return fail(AZG_EINVAL, "engine was created for the discrete variant");
     return run_search(e, B, d_root_state, nullptr, n_rollouts, tree_id0, (cudaStream_t)stream);
+}
+
+extern "C" int azg_profile_search(azg_engine* e, int32_t B, const double* d_root_state, const int32_t* d_root_n_init,
+                                  int32_t n_rollouts, int64_t tree_id0, void* stream, float ms_out[3], int32_t launches_out[3]) {
+    if (!e || !d_root_state || !ms_out || !launches_out) return fail(AZG_EINVAL, "null argument");
+    if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
+    if (n_rollouts < 1 || n_rollouts > e->cfg.max_rollouts) return fail(AZG_EINVAL, "n_rollouts out of range");
+    if (!e->weights_set && !e->tapeV) return fail(AZG_EINVAL, "azg_set_weights has not been called");
+    CK(cudaSetDevice(e->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sd = e->cfg.variant == AZG_DISCRETE ? 4 : 2;
+    if (d_root_state != e->root_state)
+        CK(cudaMemcpyAsync(e->root_state, d_root_state, (size_t)B * sd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (e->cfg.variant == AZG_DISCRETE) {
+        if (d_root_n_init) CK(cudaMemcpyAsync(e->root_n_init, d_root_n_init, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        else CK(cudaMemsetAsync(e->root_n_init, 0, (size_t)B * sizeof(int32_t), st));
+    }
+    Prof prof;
+    cudaError_t ce = cudaSuccess;
+    e->launches = enqueue_search(e, B, n_rollouts, tree_id0, st, &ce, &prof);
+    cudaError_t se = cudaStreamSynchronize(st);
+    for (int k = 0; k < 3; ++k) { ms_out[k] = 0.0f; launches_out[k] = 0; }
+    for (size_t i = 0; i < prof.cls.size(); ++i) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]) == cudaSuccess) {
+            ms_out[prof.cls[i]] += ms;
+            launches_out[prof.cls[i]] += 1;
+        }
+    }
+    for (cudaEvent_t ev : prof.ev) cudaEventDestroy(ev);
+    if (ce != cudaSuccess) return fail(AZG_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(ce));
+    if (se != cudaSuccess) return fail(AZG_ECUDA, std::string("sync: ") + cudaGetErrorString(se));
+    e->last_B = B;
+    e->last_N = n_rollouts;
+    return AZG_OK;
 }
 
 extern "C" int azg_root_results(azg_engine* e, int32_t B, float* d_actions, int32_t* d_counts, double* d_Q, double* d_V_target,

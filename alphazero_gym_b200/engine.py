@@ -145,6 +145,17 @@ class SearchEngine:
                                              _ptr(out["V_target"]), _ptr(out["n_children"]), self._stream()))
         return out
 
+    def profile_search(self, root_state: torch.Tensor, n_rollouts: int, tree_id0: int = 0) -> Dict[str, Dict[str, float]]:
+        """One search with a CUDA-event pair around every kernel launch (azg_profile_search)."""
+        assert root_state.is_cuda and root_state.dtype == torch.float64 and root_state.is_contiguous()
+        B = root_state.shape[0]
+        ms, n = (C.c_float * 3)(), (C.c_int32 * 3)()
+        with torch.cuda.device(self.device):
+            check(self._lib.azg_profile_search(self._h, B, _ptr(root_state), None, n_rollouts, tree_id0, self._stream(),
+                                               C.byref(ms), C.byref(n)))
+        self.last_B = B
+        return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(("tree_step", "evaluation", "setup"))}
+
     def status(self) -> None:
         with torch.cuda.device(self.device):
             check(self._lib.azg_status(self._h, self._stream()))

@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS simulations/sec of the batched search hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A "step" is one full batched search over one batch of synthetic roots: root evaluation, n_rollouts
+simulations (backup + select + env step + leaf evaluation) and root-result extraction.
+Workload (default, BASELINE.json configs[3]): 65536 Pendulum-v0 trees per GPU x 100
+simulations, progressive widening, GMM K=2 policy, MLP 3-128-128-128 ELU, default-initialised weights
+(torch.manual_seed(34)), roots from numpy default_rng(34).  Trees are independent, so N GPUs run N shards
+with no data-path collective (weak scaling: 65536 trees per GPU).
+
+One JSON line on stdout:
+  value      whole-job sims/s, roots already resident in HBM, results left on the device (CUDA events)
+  e2e        the same through the host-buffer C-ABI call azg_search_host: pinned H2D of the roots and D2H of
+             (actions, counts, Q, V_target, n_children) inside the timed region
+  roofline   for the dominant kernel, from per-launch CUDA-event times taken live (azg_profile_search)
+  cpu_baseline  the CPU oracle (a C port of the reference search) on a bounded sample of the same workload
+`--impl reference` times that CPU port alone (the reference itself is Python + gym and cannot travel to the
+GPU box; its single-core numbers measured in the build container are in BASELINE.md / DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (variant, trees per GPU, n_rollouts)
+    "pendulum_65536x100": ("continuous", 65536, 100),
+    "cartpole_4096x50": ("discrete", 4096, 50),
+    "pendulum_32768x200": ("continuous", 32768, 200),
+    "pendulum_1024x25": ("continuous", 1024, 25),  # quick sanity size
+}
+FLOP_PER_EVAL = {"discrete": 2 * 17280, "continuous": 2 * 34048}
+
+
+def make_roots(variant: str, B: int, seed: int = 34) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    if variant == "discrete":
+        return rng.uniform(-0.05, 0.05, size=(B, 4))
+    return np.stack([rng.uniform(-np.pi, np.pi, B), rng.uniform(-1.0, 1.0, B)], 1)
+
+
+def make_weights(variant: str) -> np.ndarray:
+    from alphazero_gym_b200.network import init_policy_weights
+    if variant == "discrete":
+        return init_policy_weights(34, 4, 128, 2, 2)
+    return init_policy_weights(34, 3, 128, 3, 6)
+
+
+def engine_config(variant: str, B: int, N: int, device: int):
+    from alphazero_gym_b200.engine import EngineConfig
+    from alphazero_gym_b200._cabi import ACT_ELU, ACT_RELU, CONTINUOUS, DISCRETE
+    if variant == "discrete":  # run_discrete.yaml / MCTSDiscrete.yaml / DiscretePolicy.yaml
+        return EngineConfig(variant=DISCRETE, max_rollouts=N, max_trees=B, num_actions=2, state_dim=4, hidden=128, n_hidden=2,
+                            activation=ACT_RELU, c_uct=1.5, gamma=1.0, epsilon=0.1, device=device, seed=34)
+    return EngineConfig(variant=CONTINUOUS, max_rollouts=N, max_trees=B, num_components=2, state_dim=3, hidden=128, n_hidden=3,
+                        activation=ACT_ELU, c_uct=0.05, c_pw=1.0, kappa=0.5, gamma=1.0, epsilon=0.0, action_bound=2.0,
+                        device=device, seed=34)
+
+
+def oracle_config(variant: str, N: int):
+    from oracle import azo
+    if variant == "discrete":
+        return azo.discrete_config(n_rollouts=N, epsilon=0.1, math_mode=azo.MATH_DET)
+    return azo.continuous_config(n_rollouts=N, math_mode=azo.MATH_DET)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc, self.thread = device, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(variant: str, c: dict) -> float:
+    """Algorithmic node-table bytes of the tree-step kernels for one search:
+    select  sum_levels [4 node.n + 4 V + 4 chosen link] + children scanned * (8 W + 4 n [+4 prior]);
+    backup  sum_levels [8 r + 4 parent link + 2*(8+4) edge W,n rw + 2*4 parent n rw];
+    expansion one node row (env state + r 8 + V 4 + n 4 + links 8 [+ priors]) + edge init."""
+    per_child = 16 if variant == "discrete" else 12
+    expansions = c["sims"] - c["terminal_leaf_sims"]
+    exp_bytes = (32 + 8 + 4 + 4 + 8 + 8 + 24) if variant == "discrete" else (16 + 8 + 4 + 4 + 8 + 16)
+    return c["levels"] * (12 + 44) + c["children_scanned"] * per_child + expansions * exp_bytes
+
+
+def cpu_port_throughput(variant: str, N: int, roots: np.ndarray, weights: np.ndarray, seconds: float, threads: int):
+    """Time the CPU oracle (C port of the reference search) on a bounded sample; returns (sims/s, sample text)."""
+    from oracle import azo
+    cfg = oracle_config(variant, N)
+    n0 = min(len(roots), 32 * threads)
+    t0 = time.perf_counter()
+    azo.search(cfg, weights, roots[:n0], dump=False, n_threads=threads)
+    rate = n0 * N / (time.perf_counter() - t0)
+    n = int(max(n0, min(len(roots), rate * seconds / N)))
+    t0 = time.perf_counter()
+    azo.search(cfg, weights, roots[:n], dump=False, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n * N / dt, f"first {n} trees x {N} sims of the workload, {threads} threads, {dt:.1f} s"
+
+
+def run_reference(args, variant, B, N, rank, world):
+    """--impl reference: the CPU port on all host cores, each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from oracle import azo
+    threads = os.cpu_count() or 1
+    roots, weights = make_roots(variant, B), make_weights(variant)
+    cfg = oracle_config(variant, N)
+    # size one step to ~ (120 s budget) / (steps + warmup)
+    n0 = min(B, 32 * threads)
+    t0 = time.perf_counter()
+    azo.search(cfg, weights, roots[:n0], dump=False, n_threads=threads)
+    rate = n0 * N / (time.perf_counter() - t0)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    n = int(max(n0, min(B, rate * budget / N)))
+    for _ in range(args.warmup):
+        azo.search(cfg, weights, roots[:n], dump=False, n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        azo.search(cfg, weights, roots[:n], dump=False, n_threads=threads)
+    dt = time.perf_counter() - t0
+    v = n * N * args.steps / dt
+    sample = f"{n} of {B} trees x {N} sims per step, {threads} threads"
+    line = {"impl": "reference", "metric": "MCTS simulations/sec (batched trees)", "value": v, "unit": "sims/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 tree statistics / f32 network", "data": "synthetic",
+            "config": {"workload": args.workload, "trees_per_step": n, "n_rollouts": N,
+                       "note": "CPU C port (oracle/azg_oracle.c) of the reference's python search; the python reference cannot travel"},
+            "cpu_baseline": {"value": v, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pendulum_65536x100", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    variant, B, N = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, variant, B, N, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from alphazero_gym_b200.engine import SearchEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    tree_id0 = rank * B  # global tree ids: shard r owns trees [r*B, (r+1)*B)
+    roots_h = make_roots(variant, B * world)[rank * B:(rank + 1) * B].copy()
+    weights = make_weights(variant)
+    eng = SearchEngine(engine_config(variant, B, N, local))
+    eng.set_weights(weights)
+    roots_d = torch.from_numpy(roots_h).cuda()
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        eng.search(roots_d, N, tree_id0=tree_id0)
+        res = eng.root_results()
+    eng.status()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.search(roots_d, N, tree_id0=tree_id0)
+        res = eng.root_results()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    eng.status()
+    counters = eng.counters()
+    launches_per_step = counters["launches"] + 1  # + the root-results kernel
+
+    # ---- end to end through the host-buffer C-ABI entry point ("e2e") -------------------------------
+    for _ in range(2):
+        out = eng.search_host(roots_h, N, tree_id0=tree_id0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = eng.search_host(roots_h, N, tree_id0=tree_id0)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    checksum = int(out["counts"].sum())
+    assert checksum == B * N, f"visit counts do not add up: {checksum} != {B * N}"
+    h2d = roots_h.nbytes
+    d2h = sum(out[k].nbytes for k in ("actions", "counts", "Q", "V_target", "n_children"))
+
+    # ---- per-kernel times, live, for the roofline ----------------------------------------------------
+    eng.profile_search(roots_d, N, tree_id0=tree_id0)
+    prof = eng.profile_search(roots_d, N, tree_id0=tree_id0)
+    pc = eng.counters()
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    ev, tr = prof["evaluation"], prof["tree_step"]
+    fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    ev_avg_ms = ev["ms"] / max(1, ev["launches"])
+    tr_avg_ms = tr["ms"] / max(1, tr["launches"])
+    ev_tflops = FLOP_PER_EVAL[variant] * B / (ev_avg_ms * 1e-3) / 1e12
+    tr_bytes = algorithmic_bytes(variant, pc) / max(1, tr["launches"])
+    tr_gbs = tr_bytes / (tr_avg_ms * 1e-3) / 1e9
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(args.workload, {})
+    roof_eval = {"kernel": "k_mlp (leaf evaluation)", "bound": "fp32", "achieved": ev_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                 "frac": ev_tflops / fp32_peak, "traffic": traffic.get("k_mlp"),
+                 "peak_source": f"{sm_count} SMs x 128 FMA/clk x 2 x {sm_max_mhz:.0f} MHz (CUDA-core FP32; the 1e-5 parity tolerance rules out TF32/BF16 tensor products)",
+                 "avg_launch_ms": ev_avg_ms, "launches": ev["launches"], "flop_per_launch": FLOP_PER_EVAL[variant] * B,
+                 "share_of_step": ev["ms"] / (ev["ms"] + tr["ms"] + prof["setup"]["ms"])}
+    roof_tree = {"kernel": "k_step (backup + select + expansion/env step)", "bound": "hbm", "achieved": tr_gbs, "peak": hbm_peak,
+                 "unit": "GB/s", "frac": tr_gbs / hbm_peak, "traffic": traffic.get("k_step"), "peak_source": peak_src,
+                 "avg_launch_ms": tr_avg_ms, "launches": tr["launches"], "algorithmic_bytes_per_launch": tr_bytes,
+                 "algorithmic_bytes_per_sim": algorithmic_bytes(variant, pc) / max(1, pc["sims"]),
+                 "share_of_step": tr["ms"] / (ev["ms"] + tr["ms"] + prof["setup"]["ms"])}
+    dominant = roof_eval if ev["ms"] >= tr["ms"] else roof_tree
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sample = cpu_port_throughput(variant, N, roots_h, weights, args.cpu_seconds, threads)
+        cpu = {"value": v, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample}
+
+    # ---- max over ranks ---------------------------------------------------------------------------------------
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    total_sims = world * B * N * args.steps
+    if rank == 0:
+        line = {
+            "metric": "MCTS simulations/sec (batched trees)", "value": total_sims / (ms_max * 1e-3), "unit": "sims/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 tree statistics + env dynamics / f32 network", "data": "synthetic",
+            "config": {"workload": args.workload, "env": "Pendulum-v0" if variant == "continuous" else "CartPole-v0",
+                       "trees_per_gpu": B, "global_trees": B * world, "n_rollouts": N, "parallelism": f"tree-sharded x{world}, no data-path collective",
+                       "weights": "default init, torch.manual_seed(34)", "roots": "numpy default_rng(34)",
+                       "l2": "node tables per GPU (%.0f MB) exceed the 126 MB L2; no explicit flush" % (eng.rows * B * (32 + 16 + 32) / 1e6)
+                       if variant == "continuous" else "tables are L2-resident at this size (SURVEY 8d config 3); no explicit flush"},
+            "e2e": {"value": total_sims / (e2e_ms_max * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms_max / args.steps, "api": "azg_search_host via SearchEngine.search_host (wall clock between syncs)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clk,
+            "roofline": dominant,
+            "roofline_all": {"evaluation": roof_eval, "tree_step": roof_tree},
+            "counters_per_sim": {k: pc[k] / max(1, pc["sims"]) for k in ("levels", "children_scanned", "pw_inserts", "evals")},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,12 @@ int azg_dump_tree_continuous(azg_engine* e, int32_t B, const azg_dump_continuous
  * ended on a terminal node, [7] kernels launched (or graph nodes replayed). */
 int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]);
 
+/* Measurement hook: runs one search with direct launches, a CUDA-event pair around every kernel, and
+ * returns total milliseconds and launch counts per kernel class: [0] tree step kernels (backup + select +
+ * expansion/env step), [1] leaf evaluation (network), [2] setup (root init / root insert).  Synchronous. */
+int azg_profile_search(azg_engine* e, int32_t B, const double* d_root_state, const int32_t* d_root_n_init,
+                       int32_t n_rollouts, int64_t tree_id0, void* stream, float ms_out[3], int32_t launches_out[3]);
+
 /* Batched network forward on its own (known-answer tests of the evaluation kernel):
  * d_x [n][state_dim] -> d_V [n], d_head [n][azg_head_dim(e)] post-processed head
  * (discrete: softmax priors [A]; continuous: mu[K], sigma[K], prob[K]). */
