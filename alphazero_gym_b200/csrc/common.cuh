@@ -4,10 +4,10 @@
 // (tree t owns rows [t*R, (t+1)*R), R = max_rollouts + 2).  The reference's pointer-linked
 // Node / Action objects (alphazero/search/states.py:8-112) become:
 //   * one packed HOT row per node, sized to DRAM sectors so a random node visit costs whole sectors
-//     only: 64 B for the discrete tree (node + its A=2 edges), 32 B for the continuous tree (edge + the
-//     child node it leads to -- edges and non-root nodes are 1:1);
-//   * COLD structure-of-arrays side tables that select/backup never touch: env state, cached policy
-//     head, and (continuous) a byte-per-row parent array that is scanned coalesced to enumerate children.
+//     only: 64 B for the discrete tree (node + its A=2 edges) and 64 B for the continuous tree (sector 0:
+//     edge statistics + the child node it leads to -- edges and non-root nodes are 1:1, SURVEY 7-4;
+//     sector 1: that node's inline child list).  64 B is also the DRAM burst, so a row miss wastes nothing;
+//   * COLD structure-of-arrays side tables that select/backup never touch: env state, cached policy head.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,19 +33,24 @@ static_assert(sizeof(DRow) == 64, "discrete row must be two 32 B sectors");
 #define DROW_NONE 0xFFFFu
 
 struct __align__(16) CRow {  // ActionContinuous + the NodeContinuous it leads to (states.py:194-289, :365-433)
+    // sector 0 -- read for every child scanned by UCT and rewritten by backup
     double W;                // Action.W
     double r;                // child Node.r (already / PENDULUM_R_SCALE)
     float V;                 // child Node.V
     float action;            // Action.action
     int32_t n_e;             // Action.n
     uint32_t nn_flags;       // child Node.n in bits 0..23 | CROW_EXPANDED | CROW_TERMINAL
+    // sector 1 -- the child node's own child_actions list, in insertion order; read only when the
+    // descent enters this node, appended to by progressive widening
+    uint8_t kids[31];        // row indices
+    uint8_t nkids;
 };
-static_assert(sizeof(CRow) == 32, "continuous row must be one 32 B sector");
+static_assert(sizeof(CRow) == 64, "continuous row must be two 32 B sectors (one 64 B DRAM burst)");
+#define CROW_MAX_KIDS 31
 #define ROW_TERMINAL 1u
 #define CROW_NMASK 0x00FFFFFFu
 #define CROW_EXPANDED 0x01000000u
 #define CROW_TERMINAL 0x02000000u
-#define CPARENT_NONE 0xFFu
 
 // leaf word handed from the tree kernels to the evaluation kernel
 #define LEAF_ROW_MASK 0xFFFF
@@ -69,8 +74,7 @@ struct TreeParams {
     CRow* crows;      // [B][R]
     double2* cstate;  // [B][R]   (th, thdot)
     float* chead;     // [B][R][HS]  mu[K], sigma[K], prob[K]
-    uint8_t* cparent; // [B][PSTRIDE]
-    int32_t PSTRIDE;
+    double* leafR;    // [B] return at the leaf edge of the current simulation: r + gamma*V (continuous)
     const int32_t* pw_table;  // [max_rollouts + 2]  ceil(c_pw * (n+1)^kappa), built on the host
     // per-tree scalars
     int32_t* n_rows;  // rows / nodes in use

@@ -36,7 +36,7 @@ static int fail(int code, const std::string& msg) {
 
 struct azg_engine {
     azg_config cfg;
-    int R = 0, HS = 0, P = 0, PO_PAD = 0, L = 0, PW = 0, PSTRIDE = 0, cmax = 0, K3 = 0;
+    int R = 0, HS = 0, P = 0, PO_PAD = 0, cmax = 0, K3 = 0;
     int64_t n_weights = 0;
     int wcount = 0;
     size_t mlp_smem = 0;
@@ -47,7 +47,7 @@ struct azg_engine {
     CRow* crows = nullptr;
     double2* cstate = nullptr;
     float* chead = nullptr;
-    uint8_t* cparent = nullptr;
+    double* leafR = nullptr;
     int32_t *pw_table = nullptr, *n_rows = nullptr, *draws = nullptr, *pw = nullptr, *depth = nullptr, *leaf = nullptr;
     uint8_t* path = nullptr;
     uint32_t* ctr = nullptr;
@@ -93,7 +93,7 @@ extern "C" void azg_destroy(azg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
-    void* ptrs[] = {e->drows, e->dstate, e->crows, e->cstate, e->chead, e->cparent, e->pw_table, e->n_rows, e->draws, e->pw,
+    void* ptrs[] = {e->drows, e->dstate, e->crows, e->cstate, e->chead, e->leafR, e->pw_table, e->n_rows, e->draws, e->pw,
                     e->depth, e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
@@ -156,19 +156,10 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
             if (n <= c.max_rollouts) cm = std::max(cm, pwt.back());
         }
         e->cmax = cm + 1;
-        // sub-warp width: enough lanes for the widest child list and for the parent bytes (4*PW rows per lane)
-        int L = 8;
-        while (L < cm) L *= 2;
-        int PW = 1;
-        while (L * 4 * PW < (int)R && PW < 4) PW *= 2;
-        while (L * 4 * PW < (int)R && L < 32) L *= 2;
-        if (L > 32 || L * 4 * PW < (int)R || cm > L) {
+        if (cm + 1 > CROW_MAX_KIDS) {
             delete e;
-            return fail(AZG_ECAPACITY, "progressive-widening fan-out or row count exceeds a warp (c_pw/kappa/n_rollouts too large)");
+            return fail(AZG_ECAPACITY, "progressive-widening fan-out exceeds the 31 inline child slots of a row (c_pw/kappa/n_rollouts too large)");
         }
-        e->L = L;
-        e->PW = PW;
-        e->PSTRIDE = L * 4 * PW;
     } else {
         e->cmax = c.num_actions;
     }
@@ -188,7 +179,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
         ALLOC(crows, B * R);
         ALLOC(cstate, B * R);
         ALLOC(chead, B * R * e->HS);
-        ALLOC(cparent, B * e->PSTRIDE);
+        ALLOC(leafR, B);
         ALLOC(pw_table, pwt.size());
         ALLOC(path, B * R);
         CK(cudaMemcpy(e->pw_table, pwt.data(), pwt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -297,7 +288,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.gamma_f32 = (float)c.gamma; p.action_bound = c.action_bound;
     p.seed = c.seed; p.tree_id0 = tree_id0;
     p.drows = e->drows; p.dstate = e->dstate;
-    p.crows = e->crows; p.cstate = e->cstate; p.chead = e->chead; p.cparent = e->cparent; p.PSTRIDE = e->PSTRIDE;
+    p.crows = e->crows; p.cstate = e->cstate; p.chead = e->chead; p.leafR = e->leafR;
     p.pw_table = e->pw_table;
     p.n_rows = e->n_rows; p.draws = e->draws; p.pw = e->pw; p.depth = e->depth; p.leaf = e->leaf; p.path = e->path;
     p.ctr = e->ctr; p.X = e->X; p.root_state = e->root_state; p.root_n_init = e->root_n_init; p.err = e->err;
@@ -314,6 +305,7 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     m.variant = c.variant; m.A = c.num_actions; m.K = c.num_components; m.R = e->R; m.HS = e->HS;
     m.ls_min = c.log_std_min; m.ls_max = c.log_std_max;
     m.leaf = e->leaf; m.drows = e->drows; m.crows = e->crows; m.chead = e->chead; m.evals = e->ctr + (size_t)3 * n;
+    m.leafR = e->leafR; m.gamma_f32 = (float)c.gamma;
     m.head_dim = azg_head_dim(e);
     return m;
 }
@@ -328,16 +320,8 @@ static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStrea
 
 template <bool BK, bool SEL>
 static cudaError_t launch_step_continuous(const azg_engine* e, const TreeParams& p, cudaStream_t st) {
-    const int grid = (p.B + TREES_PER_CTA - 1) / TREES_PER_CTA;
-    if (e->L == 8 && e->PW == 1) k_step_continuous<8, 1, BK, SEL><<<grid, TREES_PER_CTA * 8, 0, st>>>(p);
-    else if (e->L == 8 && e->PW == 2) k_step_continuous<8, 2, BK, SEL><<<grid, TREES_PER_CTA * 8, 0, st>>>(p);
-    else if (e->L == 8 && e->PW == 4) k_step_continuous<8, 4, BK, SEL><<<grid, TREES_PER_CTA * 8, 0, st>>>(p);
-    else if (e->L == 16 && e->PW == 1) k_step_continuous<16, 1, BK, SEL><<<grid, TREES_PER_CTA * 16, 0, st>>>(p);
-    else if (e->L == 16 && e->PW == 2) k_step_continuous<16, 2, BK, SEL><<<grid, TREES_PER_CTA * 16, 0, st>>>(p);
-    else if (e->L == 16 && e->PW == 4) k_step_continuous<16, 4, BK, SEL><<<grid, TREES_PER_CTA * 16, 0, st>>>(p);
-    else if (e->L == 32 && e->PW == 1) k_step_continuous<32, 1, BK, SEL><<<grid, TREES_PER_CTA * 32, 0, st>>>(p);
-    else if (e->L == 32 && e->PW == 2) k_step_continuous<32, 2, BK, SEL><<<grid, TREES_PER_CTA * 32, 0, st>>>(p);
-    else k_step_continuous<32, 4, BK, SEL><<<grid, TREES_PER_CTA * 32, 0, st>>>(p);
+    (void)e;
+    k_step_continuous<BK, SEL><<<(p.B + 127) / 128, 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -386,7 +370,6 @@ static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStr
         }
         LK(0, (k_step_discrete<true, false><<<tg, tb, 0, st>>>(p)));
     } else {
-        if (ce == cudaSuccess) ce = cudaMemsetAsync(e->cparent, 0xFF, (size_t)B * e->PSTRIDE, st);
         LK(2, (k_init_continuous<<<tg, tb, 0, st>>>(p)));
         if (!tape) LK(1, ce = launch_mlp(e, m, st));
         LK(2, (k_root_insert_continuous<<<tg, tb, 0, st>>>(p)));
@@ -653,25 +636,32 @@ extern "C" int azg_dump_tree_continuous(azg_engine* e, int32_t B, const azg_dump
     if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaDeviceSynchronize());
-    const size_t R = e->R, K3 = e->K3, HS = e->HS, PS = e->PSTRIDE;
+    const size_t R = e->R, K3 = e->K3, HS = e->HS;
     std::vector<CRow> rows((size_t)B * R);
     std::vector<double2> st((size_t)B * R);
     std::vector<float> hd((size_t)B * R * HS);
-    std::vector<uint8_t> par((size_t)B * PS);
     std::vector<int32_t> nr(B);
     CK(cudaMemcpy(rows.data(), e->crows, rows.size() * sizeof(CRow), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(st.data(), e->cstate, st.size() * sizeof(double2), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hd.data(), e->chead, hd.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(par.data(), e->cparent, par.size(), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(nr.data(), e->n_rows, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> par(R);
     for (size_t t = 0; t < (size_t)B; ++t) {
         o->n_rows[t] = nr[t];
+        // parent links are implicit in the inline child lists
+        for (size_t i = 0; i < R; ++i) par[i] = -1;
+        for (size_t i = 0; i < R && (int)i < nr[t]; ++i) {
+            const CRow& r = rows[t * R + i];
+            if (!(r.nn_flags & CROW_EXPANDED)) continue;
+            for (int k = 0; k < r.nkids && k < CROW_MAX_KIDS; ++k)
+                if (r.kids[k] < R) par[r.kids[k]] = (int32_t)i;
+        }
         for (size_t i = 0; i < R; ++i) {
             const size_t q = t * R + i;
             const bool live = (int)i < nr[t];
             const CRow& r = rows[q];
             const bool ex = live && (r.nn_flags & CROW_EXPANDED);
-            o->parent[q] = live ? (i == 0 ? -1 : par[t * PS + i]) : 0;
+            o->parent[q] = live ? par[i] : 0;
             o->action[q] = live && i > 0 ? r.action : 0.0f;
             o->eW[q] = live ? r.W : 0.0;
             o->en[q] = live ? r.n_e : 0;

@@ -37,6 +37,8 @@ struct MlpParams {
     CRow* crows;
     float* chead;
     uint32_t* evals;     // per-tree evaluation counter
+    double* leafR;       // continuous: leafR[t] += gamma_f32 * V  (first backup step, mcts.py:260-263)
+    float gamma_f32;
     float* outV;
     float* outHead;
     int32_t head_dim;
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__((MLP_TM / 8) * (H / 8), 1) k_mlp(const MlpPara
                     *reinterpret_cast<float2*>(d->prior) = make_float2(post[0], post[1]);
                 } else {
                     p.crows[ri].V = V;
+                    p.leafR[gr] = p.leafR[gr] + (double)__fmul_rn(p.gamma_f32, V);
                     float* h = p.chead + ri * p.HS;
                     for (int i = 0; i < npost; ++i) h[i] = post[i];
                 }
