@@ -89,6 +89,8 @@ static cudaError_t dalloc(T** p, size_t n) {
     return cudaMalloc((void**)p, n * sizeof(T));
 }
 
+static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr);
+
 extern "C" void azg_destroy(azg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
@@ -197,8 +199,11 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     CK(cudaMemset(e->err, 0, sizeof(int32_t)));
     CK(cudaMemset(e->n_rows, 0, B * sizeof(int32_t)));
     CK(cudaMemset(e->ctr, 0, 4 * B * sizeof(uint32_t)));
-    CK(cudaFuncSetAttribute(k_mlp<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
-    CK(cudaFuncSetAttribute(k_mlp<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+    {
+        MlpParams dummy;
+        memset(&dummy, 0, sizeof dummy);
+        CK(launch_mlp(e, dummy, nullptr, true));
+    }
     e->h_pinned_bytes = B * 4 * sizeof(double) + B * sizeof(int32_t) +
                         B * e->cmax * (sizeof(float) + sizeof(int32_t) + sizeof(double)) + B * (sizeof(double) + sizeof(int32_t)) + 256;
     CK(cudaMallocHost(&e->h_pinned, e->h_pinned_bytes));
@@ -300,8 +305,8 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     MlpParams m;
     memset(&m, 0, sizeof m);
     const azg_config& c = e->cfg;
-    m.wpack = e->wpack; m.wcount = e->wcount; m.S = c.state_dim; m.L = c.n_hidden; m.P = e->P; m.PO_PAD = e->PO_PAD;
-    m.act = c.activation; m.n = n; m.X = reinterpret_cast<const float*>(e->X); m.xstride = 4; m.mode = 0;
+    m.wpack = e->wpack; m.wcount = e->wcount; m.L = c.n_hidden; m.P = e->P; m.PO_PAD = e->PO_PAD;
+    m.n = n; m.X = reinterpret_cast<const float*>(e->X); m.xstride = 4; m.mode = 0;
     m.variant = c.variant; m.A = c.num_actions; m.K = c.num_components; m.R = e->R; m.HS = e->HS;
     m.ls_min = c.log_std_min; m.ls_max = c.log_std_max;
     m.leaf = e->leaf; m.drows = e->drows; m.crows = e->crows; m.chead = e->chead; m.evals = e->ctr + (size_t)3 * n;
@@ -310,12 +315,23 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     return m;
 }
 
-static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStream_t st) {
-    const int tiles = (m.n + MLP_TM - 1) / MLP_TM;
-    const int grid = std::max(1, std::min(tiles, e->sm_count));
-    if (e->cfg.hidden == 128) k_mlp<128><<<grid, (MLP_TM / 8) * (128 / 8), e->mlp_smem, st>>>(m);
-    else k_mlp<64><<<grid, (MLP_TM / 8) * (64 / 8), e->mlp_smem, st>>>(m);
+template <int H, int S, int ACT>
+static cudaError_t launch_mlp_t(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr) {
+    if (set_attr) return cudaFuncSetAttribute(k_mlp<H, S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mlp_smem);
+    const int units = (m.n + MLP_UNIT - 1) / MLP_UNIT;
+    const int grid = std::max(1, std::min((units + 1) / 2, e->sm_count));
+    k_mlp<H, S, ACT><<<grid, 16 * (H / 8), e->mlp_smem, st>>>(m);
     return cudaGetLastError();
+}
+
+static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr) {
+    const int H = e->cfg.hidden, S = e->cfg.state_dim, A = e->cfg.activation;
+#define MLP_CASE(h, s, a) \
+    if (H == h && S == s && A == a) return launch_mlp_t<h, s, a>(e, m, st, set_attr);
+    MLP_CASE(128, 4, 0) MLP_CASE(128, 4, 1) MLP_CASE(128, 3, 0) MLP_CASE(128, 3, 1)
+    MLP_CASE(64, 4, 0) MLP_CASE(64, 4, 1) MLP_CASE(64, 3, 0) MLP_CASE(64, 3, 1)
+#undef MLP_CASE
+    return cudaErrorInvalidValue;
 }
 
 template <bool BK, bool SEL>
@@ -362,21 +378,21 @@ static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStr
     const int tb = 128, tg = (B + tb - 1) / tb;
     if (e->cfg.variant == AZG_DISCRETE) {
         LK(2, (k_init_discrete<<<tg, tb, 0, st>>>(p)));
-        if (!tape) LK(1, ce = launch_mlp(e, m, st));
+        if (!tape) LK(1, ce = launch_mlp(e, m, st, false));
         for (int it = 0; it < N; ++it) {
             if (it == 0) LK(0, (k_step_discrete<false, true><<<tg, tb, 0, st>>>(p)));
             else LK(0, (k_step_discrete<true, true><<<tg, tb, 0, st>>>(p)));
-            if (!tape) LK(1, ce = launch_mlp(e, m, st));
+            if (!tape) LK(1, ce = launch_mlp(e, m, st, false));
         }
         LK(0, (k_step_discrete<true, false><<<tg, tb, 0, st>>>(p)));
     } else {
         LK(2, (k_init_continuous<<<tg, tb, 0, st>>>(p)));
-        if (!tape) LK(1, ce = launch_mlp(e, m, st));
+        if (!tape) LK(1, ce = launch_mlp(e, m, st, false));
         LK(2, (k_root_insert_continuous<<<tg, tb, 0, st>>>(p)));
         for (int it = 0; it < N; ++it) {
             if (it == 0) LK(0, ce = (launch_step_continuous<false, true>(e, p, st)));
             else LK(0, ce = (launch_step_continuous<true, true>(e, p, st)));
-            if (!tape) LK(1, ce = launch_mlp(e, m, st));
+            if (!tape) LK(1, ce = launch_mlp(e, m, st, false));
         }
         LK(0, ce = (launch_step_continuous<true, false>(e, p, st)));
     }
@@ -686,7 +702,7 @@ extern "C" int azg_mlp_forward(azg_engine* e, int32_t n, const float* d_x, float
     CK(cudaSetDevice(e->cfg.device));
     MlpParams m = make_mlp_params(e, n);
     m.X = d_x; m.xstride = e->cfg.state_dim; m.mode = 1; m.outV = d_V; m.outHead = d_head; m.evals = nullptr;
-    CK(launch_mlp(e, m, (cudaStream_t)stream));
+    CK(launch_mlp(e, m, (cudaStream_t)stream, false));
     return AZG_OK;
 }
 
