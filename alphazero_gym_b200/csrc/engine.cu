@@ -320,7 +320,7 @@ static cudaError_t launch_mlp_t(const azg_engine* e, const MlpParams& m, cudaStr
     if (set_attr) return cudaFuncSetAttribute(k_mlp<H, S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mlp_smem);
     const int units = (m.n + MLP_UNIT - 1) / MLP_UNIT;
     const int grid = std::max(1, std::min((units + 1) / 2, e->sm_count));
-    k_mlp<H, S, ACT><<<grid, 16 * (H / 8), e->mlp_smem, st>>>(m);
+    k_mlp<H, S, ACT><<<grid, MLP_THREADS(H), e->mlp_smem, st>>>(m);
     return cudaGetLastError();
 }
 

@@ -10,15 +10,15 @@
 // x[k], acc) for k ascending -- makes every output bit-reproducible by the CPU oracle.  A register-tiled
 // SGEMM has exactly that per-output order as long as k is the outer loop.
 //
-// Structure (one persistent CTA per SM, 256 threads for H = 128):
+// Structure (one persistent CTA per SM, 512 threads for H = 128):
 //   * all weights (138 KB for 3x128 ELU, 71 KB for 2x128 ReLU) are staged in shared memory once per CTA
 //     with TMA bulk copies (cp.async.bulk + mbarrier) and reused for every pass of the CTA;
-//   * rows are dealt to CTAs in units of 64 and processed in passes of 128 rows (8x8 register tile per
-//     thread) plus at most one 64-row pass (8x4 tile), so 65536 rows on 148 SMs cost 3.5 pass-times
-//     instead of the 4 that fixed 128-row tiles would;
+//   * rows are dealt to CTAs in units of 64 and processed in passes of 128 rows plus at most one 64-row
+//     pass (half of the warps), so 65536 rows on 148 SMs cost 3.5 pass-times instead of the 4 that fixed
+//     128-row tiles would;
 //   * activations live in shared memory k-major ([H][128]); both operands of the register tile are read
 //     with conflict-free LDS.128 and the K loop is software-pipelined (operands of k+1 are in flight while
-//     the 64 FFMAs of k issue);
+//     the FMAs of k issue);
 //   * activations are branch-free (ELU through the deterministic expm1 of detmath.cuh).
 // Bound: FP32 FMA issue (2*H*H flop per row per hidden layer).
 #pragma once
@@ -104,49 +104,63 @@ __device__ __forceinline__ void softmax_seq(const float* l, int n, float* p) {
     for (int i = 0; i < n; ++i) p[i] = __fdiv_rn(p[i], s);
 }
 
-// one hidden layer on a pass of 128 (HALF = false) or 64 (HALF = true) rows: act[H][TM] <- act(W act + b)
+// Thread mapping of the hidden layers: a pass is 128 rows x H columns; each thread owns 4 rows x 8 columns,
+// a warp owns a 32 x 32 square (8 row groups x 4 column groups), the CTA has 4 x (H/32) warps = 512 threads
+// for H = 128, i.e. 4 warps per SM sub-partition to cover LDS latency and barrier skew (the first version
+// ran 8x8 tiles on 256 threads = 2 warps per scheduler and idled 40 % of its issue slots).  Per k a warp
+// reads 128 B of activations (LDS.128, 8 distinct lanes, rest broadcast) and 2 x 64 B of weights.
+// The accumulators are float2 column pairs updated with the packed fma.rn.f32x2 (SASS FFMA2, scalar operand
+// broadcast): half the issue slots of scalar FFMA for the same IEEE result per element, which leaves slots
+// for the LDS / activation instructions.  k is the outer loop, so every output still sums in k order.
+#define MLP_THREADS(H) (128 * ((H) / 32))
+
 template <int H, int ACT, bool HALF>
 __device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const float* __restrict__ b, float* actb, int tid) {
     constexpr int TM = MLP_TM;
-    constexpr int NR = HALF ? 4 : 8;
-    const int tx = tid % 16, ty = tid / 16;  // rows {tx*4..+3, 64+tx*4..+3}, cols ty*8..+7
-    float acc[8][NR];
+    const int lane = tid & 31, wid = tid >> 5;
+    const int wr = wid / (H / 32), wc = wid % (H / 32);  // warp row block (32 rows) / column block (32 cols)
+    const int row0 = wr * 32 + (lane & 7) * 4, col0 = wc * 32 + (lane >> 3) * 8;
+    const bool active = !HALF || wr < 2;  // a 64-row pass uses warp rows 0 and 1 (warps 0..2*H/32-1: all 4 schedulers)
+    float2 acc[4][4];                     // [row][column pair]
+    if (active) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float bc = b[ty * 8 + c];
+        for (int c = 0; c < 4; ++c) {
+            const float2 bc = *reinterpret_cast<const float2*>(b + col0 + 2 * c);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[c][r] = bc;
-    }
-    const float* ap = actb + tx * 4;
-    const float* wp = Wt + ty * 8;
-    float4 a0 = *reinterpret_cast<const float4*>(ap);
-    float4 a1 = HALF ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(ap + 64);
-    float4 w0 = *reinterpret_cast<const float4*>(wp);
-    float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
-#pragma unroll 4
-    for (int k = 0; k < H; ++k) {
-        const int kn = k + 1 < H ? k + 1 : k;  // the last iteration re-reads row k (discarded)
-        const float4 na0 = *reinterpret_cast<const float4*>(ap + kn * TM);
-        const float4 na1 = HALF ? a1 : *reinterpret_cast<const float4*>(ap + kn * TM + 64);
-        const float4 nw0 = *reinterpret_cast<const float4*>(wp + kn * H);
-        const float4 nw1 = *reinterpret_cast<const float4*>(wp + kn * H + 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            for (int r = 0; r < 4; ++r) acc[r][c] = bc;
+        }
+        const float* ap = actb + row0;
+        const float* wp = Wt + col0;
+        float4 a = *reinterpret_cast<const float4*>(ap);
+        float4 w0 = *reinterpret_cast<const float4*>(wp);
+        float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+#pragma unroll 8
+        for (int k = 0; k < H; ++k) {
+            const int kn = k + 1 < H ? k + 1 : k;  // the last iteration re-reads row k (discarded)
+            const float4 na = *reinterpret_cast<const float4*>(ap + kn * TM);
+            const float4 nw0 = *reinterpret_cast<const float4*>(wp + kn * H);
+            const float4 nw1 = *reinterpret_cast<const float4*>(wp + kn * H + 4);
+            const float ar[4] = {a.x, a.y, a.z, a.w};
+            const float2 wpair[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+            for (int r = 0; r < 4; ++r) {
+                const float2 av = make_float2(ar[r], ar[r]);
 #pragma unroll
-            for (int r = 0; r < NR; ++r) acc[c][r] = __fmaf_rn(ww[c], a[r], acc[c][r]);
-        a0 = na0; a1 = na1; w0 = nw0; w1 = nw1;
+                for (int c = 0; c < 4; ++c) acc[r][c] = __ffma2_rn(av, wpair[c], acc[r][c]);
+            }
+            a = na; w0 = nw0; w1 = nw1;
+        }
     }
     __syncthreads();  // everyone has finished reading this layer's input
+    if (active) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float* dst = actb + (ty * 8 + c) * TM + tx * 4;
-        *reinterpret_cast<float4*>(dst) =
-            make_float4(mlp_act<ACT>(acc[c][0]), mlp_act<ACT>(acc[c][1]), mlp_act<ACT>(acc[c][2]), mlp_act<ACT>(acc[c][3]));
-        if (!HALF)
-            *reinterpret_cast<float4*>(dst + 64) = make_float4(mlp_act<ACT>(acc[c][NR - 4]), mlp_act<ACT>(acc[c][NR - 3]),
-                                                               mlp_act<ACT>(acc[c][NR - 2]), mlp_act<ACT>(acc[c][NR - 1]));
+        for (int c = 0; c < 4; ++c) {
+            float* d0 = actb + (col0 + 2 * c) * TM + row0;
+            *reinterpret_cast<float4*>(d0) = make_float4(mlp_act<ACT>(acc[0][c].x), mlp_act<ACT>(acc[1][c].x),
+                                                         mlp_act<ACT>(acc[2][c].x), mlp_act<ACT>(acc[3][c].x));
+            *reinterpret_cast<float4*>(d0 + TM) = make_float4(mlp_act<ACT>(acc[0][c].y), mlp_act<ACT>(acc[1][c].y),
+                                                              mlp_act<ACT>(acc[2][c].y), mlp_act<ACT>(acc[3][c].y));
+        }
     }
     __syncthreads();
 }
@@ -154,8 +168,8 @@ __device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const
 template <int H, int S, int ACT, bool HALF>
 __device__ __forceinline__ void mlp_pass(const MlpParams& p, const float* w, float* actb, float* outs, int row0, int tid) {
     constexpr int TM = MLP_TM;
-    constexpr int NT = 16 * (H / 8);
-    constexpr int NG = NT / TM;  // thread groups in the row-per-thread phases (H=128: 2, H=64: 1)
+    constexpr int NT = MLP_THREADS(H);
+    constexpr int NG = NT / TM;  // thread groups in the row-per-thread phases (H=128: 4, H=64: 2)
     constexpr int ROWS = HALF ? 64 : 128;
     const int row = tid % TM, grp = tid / TM;
     const int gr = row0 + row;
@@ -264,7 +278,7 @@ __device__ __forceinline__ void mlp_pass(const MlpParams& p, const float* w, flo
 }
 
 template <int H, int S, int ACT>
-__global__ void __launch_bounds__(16 * (H / 8), 1) k_mlp(const MlpParams p) {
+__global__ void __launch_bounds__(MLP_THREADS(H), 1) k_mlp(const MlpParams p) {
     constexpr int TM = MLP_TM;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t wbar;
