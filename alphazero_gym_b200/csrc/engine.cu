@@ -144,7 +144,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     nw += H + 1 + (int64_t)e->P * H + e->P;
     e->n_weights = nw;
     e->wcount = c.state_dim * H + H + (c.n_hidden - 1) * (H * H + H) + H * e->PO_PAD + e->PO_PAD;
-    e->mlp_smem = ((size_t)e->wcount + (size_t)H * MLP_TM + (size_t)e->PO_PAD * MLP_TM) * sizeof(float);
+    e->mlp_smem = ((size_t)e->wcount + (size_t)MLP_NGRP * (H + e->PO_PAD) * MLP_UNIT) * sizeof(float);
     if (e->mlp_smem > (size_t)prop.sharedMemPerBlockOptin) {
         delete e;
         return fail(AZG_EINVAL, "network does not fit in shared memory");
@@ -319,7 +319,7 @@ template <int H, int S, int ACT>
 static cudaError_t launch_mlp_t(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr) {
     if (set_attr) return cudaFuncSetAttribute(k_mlp<H, S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mlp_smem);
     const int units = (m.n + MLP_UNIT - 1) / MLP_UNIT;
-    const int grid = std::max(1, std::min((units + 1) / 2, e->sm_count));
+    const int grid = std::max(1, std::min((units + MLP_NGRP - 1) / MLP_NGRP, e->sm_count));
     k_mlp<H, S, ACT><<<grid, MLP_THREADS(H), e->mlp_smem, st>>>(m);
     return cudaGetLastError();
 }

@@ -12,21 +12,17 @@
 //
 // Structure (one persistent CTA per SM, 512 threads for H = 128):
 //   * all weights (138 KB for 3x128 ELU, 71 KB for 2x128 ReLU) are staged in shared memory once per CTA
-//     with TMA bulk copies (cp.async.bulk + mbarrier) and reused for every pass of the CTA;
-//   * rows are dealt to CTAs in units of 64 and processed in passes of 128 rows plus at most one 64-row
-//     pass (half of the warps), so 65536 rows on 148 SMs cost 3.5 pass-times instead of the 4 that fixed
-//     128-row tiles would;
-//   * activations live in shared memory k-major ([H][128]); both operands of the register tile are read
-//     with conflict-free LDS.128 and the K loop is software-pipelined (operands of k+1 are in flight while
-//     the FMAs of k issue);
+//     with TMA bulk copies (cp.async.bulk + mbarrier) and reused for every unit the CTA processes;
+//   * rows are dealt to CTAs in units of 32 (65536 rows = 2048 units = 13.8 per SM, so the tail is 1.2 %);
+//   * activations live in shared memory k-major ([H][32] per group); both operands of the register tile
+//     are read with conflict-free LDS.128 and the K loop is software-pipelined (operands of k+1 are in
+//     flight while the FMAs of k issue);
 //   * activations are branch-free (ELU through the deterministic expm1 of detmath.cuh).
 // Bound: FP32 FMA issue (2*H*H flop per row per hidden layer).
 #pragma once
 #include "common.cuh"
 #include "detmath.cuh"
 
-#define MLP_TM 128
-#define MLP_UNIT 64
 #define MLP_MAX_PO 28  // 1 + 3*AZG_MAX_K rounded up to a multiple of 4
 
 struct MlpParams {
@@ -104,83 +100,104 @@ __device__ __forceinline__ void softmax_seq(const float* l, int n, float* p) {
     for (int i = 0; i < n; ++i) p[i] = __fdiv_rn(p[i], s);
 }
 
-// Thread mapping of the hidden layers: a pass is 128 rows x H columns; each thread owns 4 rows x 8 columns,
-// a warp owns a 32 x 32 square (8 row groups x 4 column groups), the CTA has 4 x (H/32) warps = 512 threads
-// for H = 128, i.e. 4 warps per SM sub-partition to cover LDS latency and barrier skew (the first version
-// ran 8x8 tiles on 256 threads = 2 warps per scheduler and idled 40 % of its issue slots).  Per k a warp
-// reads 128 B of activations (LDS.128, 8 distinct lanes, rest broadcast) and 2 x 64 B of weights.
+// Thread mapping.  The CTA (512 threads for H = 128) is split into NGRP = 4 independent groups of H/32
+// warps.  A group owns a unit of 32 rows at a time: its private [H][32] activation buffer, its own named
+// barrier (bar.sync id, 128) -- never a CTA-wide __syncthreads in the steady state.  All groups share the
+// weights staged once in shared memory.  Because groups are decoupled they drift out of phase, so one
+// group's activation / head / write-back instructions fill the issue slots another group's FMA loop
+// leaves free (the lock-step 16-warp version stalled on math-pipe throttle and barriers together,
+// profiles/r1c).  Inside a group each warp owns 32 rows x 32 columns, each thread 4 rows x 8 columns; per k
+// a warp reads 128 B of activations (LDS.128, 8 distinct lanes, rest broadcast) and 2 x 64 B of weights.
 // The accumulators are float2 column pairs updated with the packed fma.rn.f32x2 (SASS FFMA2, scalar operand
-// broadcast): half the issue slots of scalar FFMA for the same IEEE result per element, which leaves slots
-// for the LDS / activation instructions.  k is the outer loop, so every output still sums in k order.
-#define MLP_THREADS(H) (128 * ((H) / 32))
+// broadcast): half the issue slots of scalar FFMA for the same IEEE result per element.  k is the outer
+// loop, so every output still sums in k order.
+#define MLP_NGRP 4
+#define MLP_UNIT 32
+#define MLP_GTHREADS(H) (32 * ((H) / 32))
+#define MLP_THREADS(H) (MLP_NGRP * MLP_GTHREADS(H))
 
-template <int H, int ACT, bool HALF>
-__device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const float* __restrict__ b, float* actb, int tid) {
-    constexpr int TM = MLP_TM;
-    const int lane = tid & 31, wid = tid >> 5;
-    const int wr = wid / (H / 32), wc = wid % (H / 32);  // warp row block (32 rows) / column block (32 cols)
-    const int row0 = wr * 32 + (lane & 7) * 4, col0 = wc * 32 + (lane >> 3) * 8;
-    const bool active = !HALF || wr < 2;  // a 64-row pass uses warp rows 0 and 1 (warps 0..2*H/32-1: all 4 schedulers)
-    float2 acc[4][4];                     // [row][column pair]
-    if (active) {
+__device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int H, int ACT>
+__device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const float* __restrict__ b, float* actg, int gt, int bar) {
+    constexpr int TU = MLP_UNIT;
+    const int lane = gt & 31, wc = gt >> 5;  // warp column block (32 cols)
+    const int row0 = (lane & 7) * 4, col0 = wc * 32 + (lane >> 3) * 8;
+#ifndef MLP_SCALAR_FMA
+    float2 acc[4][4];  // [row][column pair]
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float2 bc = *reinterpret_cast<const float2*>(b + col0 + 2 * c);
+    for (int c = 0; c < 4; ++c) {
+        const float2 bc = *reinterpret_cast<const float2*>(b + col0 + 2 * c);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r][c] = bc;
-        }
-        const float* ap = actb + row0;
-        const float* wp = Wt + col0;
-        float4 a = *reinterpret_cast<const float4*>(ap);
-        float4 w0 = *reinterpret_cast<const float4*>(wp);
-        float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+        for (int r = 0; r < 4; ++r) acc[r][c] = bc;
+    }
+#else
+    float2 acc[4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float2 bc = *reinterpret_cast<const float2*>(b + col0 + 2 * c);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r][c] = bc;
+    }
+#endif
+    const float* ap = actg + row0;
+    const float* wp = Wt + col0;
+    float4 a = *reinterpret_cast<const float4*>(ap);
+    float4 w0 = *reinterpret_cast<const float4*>(wp);
+    float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
 #pragma unroll 8
-        for (int k = 0; k < H; ++k) {
-            const int kn = k + 1 < H ? k + 1 : k;  // the last iteration re-reads row k (discarded)
-            const float4 na = *reinterpret_cast<const float4*>(ap + kn * TM);
-            const float4 nw0 = *reinterpret_cast<const float4*>(wp + kn * H);
-            const float4 nw1 = *reinterpret_cast<const float4*>(wp + kn * H + 4);
-            const float ar[4] = {a.x, a.y, a.z, a.w};
-            const float2 wpair[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+    for (int k = 0; k < H; ++k) {
+        const int kn = k + 1 < H ? k + 1 : k;  // the last iteration re-reads row k (discarded)
+        const float4 na = *reinterpret_cast<const float4*>(ap + kn * TU);
+        const float4 nw0 = *reinterpret_cast<const float4*>(wp + kn * H);
+        const float4 nw1 = *reinterpret_cast<const float4*>(wp + kn * H + 4);
+        const float ar[4] = {a.x, a.y, a.z, a.w};
+        const float2 wpair[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float2 av = make_float2(ar[r], ar[r]);
+        for (int r = 0; r < 4; ++r) {
+#ifndef MLP_SCALAR_FMA
+            const float2 av = make_float2(ar[r], ar[r]);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[r][c] = __ffma2_rn(av, wpair[c], acc[r][c]);
+            for (int c = 0; c < 4; ++c) acc[r][c] = __ffma2_rn(av, wpair[c], acc[r][c]);
+#else
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                acc[r][c].x = __fmaf_rn(ar[r], wpair[c].x, acc[r][c].x);
+                acc[r][c].y = __fmaf_rn(ar[r], wpair[c].y, acc[r][c].y);
             }
-            a = na; w0 = nw0; w1 = nw1;
+#endif
         }
+        a = na; w0 = nw0; w1 = nw1;
     }
-    __syncthreads();  // everyone has finished reading this layer's input
-    if (active) {
+    group_sync(bar, MLP_GTHREADS(H));  // the whole group has finished reading this layer's input
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float* d0 = actb + (col0 + 2 * c) * TM + row0;
-            *reinterpret_cast<float4*>(d0) = make_float4(mlp_act<ACT>(acc[0][c].x), mlp_act<ACT>(acc[1][c].x),
-                                                         mlp_act<ACT>(acc[2][c].x), mlp_act<ACT>(acc[3][c].x));
-            *reinterpret_cast<float4*>(d0 + TM) = make_float4(mlp_act<ACT>(acc[0][c].y), mlp_act<ACT>(acc[1][c].y),
-                                                              mlp_act<ACT>(acc[2][c].y), mlp_act<ACT>(acc[3][c].y));
-        }
+    for (int c = 0; c < 4; ++c) {
+        float* d0 = actg + (col0 + 2 * c) * TU + row0;
+        *reinterpret_cast<float4*>(d0) = make_float4(mlp_act<ACT>(acc[0][c].x), mlp_act<ACT>(acc[1][c].x),
+                                                     mlp_act<ACT>(acc[2][c].x), mlp_act<ACT>(acc[3][c].x));
+        *reinterpret_cast<float4*>(d0 + TU) = make_float4(mlp_act<ACT>(acc[0][c].y), mlp_act<ACT>(acc[1][c].y),
+                                                          mlp_act<ACT>(acc[2][c].y), mlp_act<ACT>(acc[3][c].y));
     }
-    __syncthreads();
+    group_sync(bar, MLP_GTHREADS(H));
 }
 
-template <int H, int S, int ACT, bool HALF>
-__device__ __forceinline__ void mlp_pass(const MlpParams& p, const float* w, float* actb, float* outs, int row0, int tid) {
-    constexpr int TM = MLP_TM;
-    constexpr int NT = MLP_THREADS(H);
-    constexpr int NG = NT / TM;  // thread groups in the row-per-thread phases (H=128: 4, H=64: 2)
-    constexpr int ROWS = HALF ? 64 : 128;
-    const int row = tid % TM, grp = tid / TM;
+// one unit of 32 rows, executed by one group of H/32 warps
+template <int H, int S, int ACT>
+__device__ __forceinline__ void mlp_unit(const MlpParams& p, const float* w, float* actg, float* outg, int row0, int gt, int bar) {
+    constexpr int TU = MLP_UNIT;
+    constexpr int NQ = MLP_GTHREADS(H) / TU;  // threads per row in the row-per-thread phases (H=128: 4)
+    const int row = gt % TU, q = gt / TU;
     const int gr = row0 + row;
     int leafw = 0;
-    bool need = row < ROWS && gr < p.n;
+    bool need = gr < p.n;
     if (need && p.mode == 0) {
         leafw = p.leaf[gr];
         need = (leafw & LEAF_EVAL) != 0;
     }
-    // ---- layer 0: S -> H, one row per thread, H/NG outputs each
-    if (row < ROWS) {
+    double lr = 0.0;
+    if (need && p.mode == 0 && p.variant == 1 && q == 0) lr = p.leafR[gr];  // in flight during the whole unit
+    // ---- layer 0: S -> H, NQ threads per row, H/NQ outputs each
+    {
         float x[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) x[s] = 0.0f;
@@ -197,47 +214,49 @@ __device__ __forceinline__ void mlp_pass(const MlpParams& p, const float* w, flo
         const float* W0 = w;
         const float* b0 = w + S * H;
 #pragma unroll 4
-        for (int j = grp * (H / NG); j < (grp + 1) * (H / NG); ++j) {
+        for (int j = q * (H / NQ); j < (q + 1) * (H / NQ); ++j) {
             float acc = b0[j];
 #pragma unroll
             for (int s = 0; s < S; ++s) acc = __fmaf_rn(W0[s * H + j], x[s], acc);
-            actb[j * TM + row] = mlp_act<ACT>(acc);
+            actg[j * TU + row] = mlp_act<ACT>(acc);
         }
     }
-    __syncthreads();
+    group_sync(bar, MLP_GTHREADS(H));
     // ---- hidden layers
     int off = S * H + H;
     for (int l = 1; l < p.L; ++l) {
-        hidden_layer<H, ACT, HALF>(w + off, w + off + H * H, actb, tid);
+        hidden_layer<H, ACT>(w + off, w + off + H * H, actg, gt, bar);
         off += H * H + H;
     }
-    // ---- heads: column 0 = value_head, columns 1..P = dist_head; one row per thread, 4 outputs per pass
-    if (row < ROWS) {
+    // ---- heads: column 0 = value_head, columns 1..P = dist_head; 4 outputs per thread and pass
+    {
         const float* Wh = w + off;
         const float* bh = Wh + H * p.PO_PAD;
-        for (int c = grp; c < p.PO_PAD / 4; c += NG) {
+        for (int c = q; c < p.PO_PAD / 4; c += NQ) {
             float4 acc = *reinterpret_cast<const float4*>(bh + c * 4);
 #pragma unroll 8
             for (int k = 0; k < H; ++k) {
-                const float a = actb[k * TM + row];
+                const float a = actg[k * TU + row];
                 const float4 w4 = *reinterpret_cast<const float4*>(Wh + k * p.PO_PAD + c * 4);
                 acc.x = __fmaf_rn(w4.x, a, acc.x);
                 acc.y = __fmaf_rn(w4.y, a, acc.y);
                 acc.z = __fmaf_rn(w4.z, a, acc.z);
                 acc.w = __fmaf_rn(w4.w, a, acc.w);
             }
-            outs[(c * 4 + 0) * TM + row] = acc.x;
-            outs[(c * 4 + 1) * TM + row] = acc.y;
-            outs[(c * 4 + 2) * TM + row] = acc.z;
-            outs[(c * 4 + 3) * TM + row] = acc.w;
+            outg[(c * 4 + 0) * TU + row] = acc.x;
+            outg[(c * 4 + 1) * TU + row] = acc.y;
+            outg[(c * 4 + 2) * TU + row] = acc.z;
+            outg[(c * 4 + 3) * TU + row] = acc.w;
         }
     }
-    __syncthreads();
-    // ---- post-processing + write-back, one row per thread (threads of group 0)
-    if (grp == 0 && need) {
-        float V = outs[row];
+    group_sync(bar, MLP_GTHREADS(H));
+    // ---- post-processing + write-back: one thread per row (warp 0 of the group); the group's other warps run
+    // ahead into the next unit's layer 0 (they only touch actg, and outg is not rewritten before two more
+    // group barriers that warp 0 takes part in)
+    if (q == 0 && need) {
+        float V = outg[row];
         float raw[3 * AZG_MAX_K], post[3 * AZG_MAX_K];
-        for (int i = 0; i < p.P; ++i) raw[i] = outs[(1 + i) * TM + row];
+        for (int i = 0; i < p.P; ++i) raw[i] = outg[(1 + i) * TU + row];
         int npost;
         if (p.variant == 0) {
             softmax_seq(raw, p.A, post);
@@ -267,32 +286,31 @@ __device__ __forceinline__ void mlp_pass(const MlpParams& p, const float* w, flo
                 *reinterpret_cast<float2*>(d->prior) = make_float2(post[0], post[1]);
             } else {
                 p.crows[ri].V = V;
-                p.leafR[gr] = p.leafR[gr] + (double)__fmul_rn(p.gamma_f32, V);
+                p.leafR[gr] = lr + (double)__fmul_rn(p.gamma_f32, V);
                 float* h = p.chead + ri * p.HS;
                 for (int i = 0; i < npost; ++i) h[i] = post[i];
             }
             p.evals[gr] += 1;
         }
     }
-    __syncthreads();  // outs / actb are reused by the next pass
 }
 
 template <int H, int S, int ACT>
 __global__ void __launch_bounds__(MLP_THREADS(H), 1) k_mlp(const MlpParams p) {
-    constexpr int TM = MLP_TM;
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t wbar;
-    float* w = smem;
-    float* actb = smem + p.wcount;  // [H][TM]
-    float* outs = actb + H * TM;    // [PO_PAD][TM]
     const int tid = threadIdx.x;
+    const int grp = tid / MLP_GTHREADS(H), gt = tid % MLP_GTHREADS(H);
+    float* w = smem;
+    float* actg = smem + p.wcount + grp * (H + p.PO_PAD) * MLP_UNIT;  // [H][32] activations of this group
+    float* outg = actg + H * MLP_UNIT;                               // [PO_PAD][32] raw head outputs
 
-    // rows are dealt in units of 64: CTA b owns units [b*u, (b+1)*u)
+    // rows are dealt in units of 32: CTA b owns units [b*per, (b+1)*per), group g takes every 4th of them
     const int units = (p.n + MLP_UNIT - 1) / MLP_UNIT;
     const int per = (units + gridDim.x - 1) / gridDim.x;
-    int unit = blockIdx.x * per;
-    const int unit_end = min(unit + per, units);
-    if (unit >= unit_end) return;
+    const int unit0 = blockIdx.x * per;
+    const int unit_end = min(unit0 + per, units);
+    if (unit0 >= unit_end) return;
 
     // stage all weights with TMA bulk copies; every thread then waits on the mbarrier
     if (tid == 0) mbar_init(&wbar, 1);
@@ -305,13 +323,6 @@ __global__ void __launch_bounds__(MLP_THREADS(H), 1) k_mlp(const MlpParams p) {
     }
     while (!mbar_try_wait(&wbar, 0)) {}
 
-    while (unit < unit_end) {
-        if (unit_end - unit >= 2) {
-            mlp_pass<H, S, ACT, false>(p, w, actb, outs, unit * MLP_UNIT, tid);
-            unit += 2;
-        } else {
-            mlp_pass<H, S, ACT, true>(p, w, actb, outs, unit * MLP_UNIT, tid);
-            unit += 1;
-        }
-    }
+    for (int unit = unit0 + grp; unit < unit_end; unit += MLP_NGRP)
+        mlp_unit<H, S, ACT>(p, w, actg, outg, unit * MLP_UNIT, gt, 1 + grp);
 }
