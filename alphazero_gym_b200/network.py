@@ -41,3 +41,63 @@ def init_policy_state_dict(seed: int, state_dim: int, hidden: int, n_hidden: int
 def init_policy_weights(seed: int, state_dim: int, hidden: int, n_hidden: int, head_dim: int) -> np.ndarray:
     sd = init_policy_state_dict(seed, state_dim, hidden, n_hidden, head_dim)
     return np.concatenate([t.numpy().astype(np.float32).ravel() for t in sd.values()])
+
+
+class PolicyNet(nn.Module):
+    """Same parameter structure (and state_dict keys) as the reference's DiscretePolicy / DiagonalNormalPolicy /
+    DiagonalGMMPolicy (alphazero/network/policies.py:163-259, :355-434, :502-588): `trunk` Sequential of
+    Linear + activation, `value_head`, `dist_head`.  Used where the reference itself cannot be imported
+    (tests and benchmarks on the GPU box); a reference model can be passed to the search classes directly."""
+
+    def __init__(self, state_dim: int, hidden: int, n_hidden: int, head_dim: int, nonlinearity: str = "relu",
+                 num_components: int = 1, num_actions: int = 0, action_bound: float = 2.0,
+                 log_param_min: float = -5.0, log_param_max: float = 2.0):
+        super().__init__()
+        act = {"relu": nn.ReLU, "elu": nn.ELU}[nonlinearity.lower()]
+        layers, d = [], state_dim
+        for _ in range(n_hidden):
+            layers += [nn.Linear(d, hidden), act()]
+            d = hidden
+        self.trunk = nn.Sequential(*layers)
+        self.value_head = nn.Linear(hidden, 1)
+        self.dist_head = nn.Linear(hidden, head_dim)
+        self.state_dim, self.num_components, self.num_actions = state_dim, num_components, num_actions
+        self.action_bound, self.log_param_min, self.log_param_max = action_bound, log_param_min, log_param_max
+        self.layernorm = False
+
+    def load_flat(self, flat: np.ndarray) -> "PolicyNet":
+        off = 0
+        with torch.no_grad():
+            for prm in self.state_dict().values():
+                n = prm.numel()
+                prm.copy_(torch.from_numpy(np.asarray(flat[off:off + n], np.float32)).reshape(prm.shape))
+                off += n
+        assert off == len(flat)
+        return self
+
+
+def describe_model(model) -> dict:
+    """Network shape the engine needs, read off a reference-style policy module (policies.py:806 make_policy
+    products or PolicyNet): trunk widths, activation, head size, mixture components, log-std clamp."""
+    if getattr(model, "layernorm", False):
+        raise NotImplementedError("layernorm=True policies are not supported by the CUDA evaluation kernel")
+    sd = model.state_dict()
+    tw = [k for k in sd if k.startswith("trunk.") and k.endswith(".weight")]
+    if not tw or "value_head.weight" not in sd or "dist_head.weight" not in sd:
+        raise TypeError("model must expose trunk.*, value_head and dist_head parameters (alphazero/network/policies.py)")
+    hidden = sd[tw[0]].shape[0]
+    for k in tw:
+        if sd[k].shape[0] != hidden:
+            raise NotImplementedError("all hidden layers must have the same width")
+    act_name = type(model.trunk[1]).__name__.lower()
+    if act_name not in ("relu", "elu"):
+        raise NotImplementedError(f"activation {act_name} is not supported (relu / elu are the configured ones)")
+    return dict(state_dim=sd[tw[0]].shape[1], hidden=hidden, n_hidden=len(tw), activation=0 if act_name == "relu" else 1,
+                head_dim=sd["dist_head.weight"].shape[0], num_components=int(getattr(model, "num_components", 1) or 1),
+                action_bound=float(getattr(model, "action_bound", None) or 0.0),
+                log_std_min=float(getattr(model, "log_param_min", -5.0)), log_std_max=float(getattr(model, "log_param_max", 2.0)))
+
+
+def weights_version(model) -> int:
+    """Cheap change detector: in-place optimizer updates bump every parameter's _version."""
+    return sum(int(p._version) + (p.data_ptr() % 1000003) for p in model.parameters())

@@ -1,0 +1,54 @@
+"""N>1 path on CPU: two processes over gloo shard a batch of trees, each runs its shard with the global
+tree ids of its range, the root-result rows are all-gathered and must equal the single-process run bit for bit.
+The per-shard searcher here is the CPU oracle (the CUDA engine takes its place on GPUs; bench.py --gpus N
+uses the same shard_range / tree_id0 logic).  Also covers the weight broadcast."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import azo, gen_golden as G
+from alphazero_gym_b200.parallel import allgather_results, broadcast_weights, results_to_torch, shard_range
+
+KEYS = ("actions", "counts", "Q", "V_target", "n_children")
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg, g = G.load("pendulum_n25_k2")
+        roots = G.pendulum_roots(total, seed=11)
+        # (C1) rank 0 owns the weights; the others start from zeros
+        w = torch.from_numpy(g["weights"].copy()) if rank == 0 else torch.zeros(len(g["weights"]))
+        broadcast_weights(w, src=0)
+        assert np.array_equal(w.numpy(), g["weights"])
+        lo, hi = shard_range(total, rank, world)
+        local = azo.search(cfg, w.numpy(), roots[lo:hi], tree_id0=lo, dump=False)
+        gathered = allgather_results(results_to_torch({k: local[k] for k in KEYS}), total)  # (C2)
+        if rank == 0:
+            np.savez(out_path, **{k: v.numpy() for k, v in gathered.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sharded_search_equals_single_process(tmp_path):
+    total, world = 21, 2  # odd on purpose: ranks own 11 and 10 trees
+    out = str(tmp_path / "gathered.npz")
+    mp.spawn(_worker, args=(world, _free_port(), total, out), nprocs=world, join=True)
+    got = np.load(out)
+    cfg, g = G.load("pendulum_n25_k2")
+    ref = azo.search(cfg, g["weights"], G.pendulum_roots(total, seed=11), tree_id0=0, dump=False)
+    for k in KEYS:
+        assert np.array_equal(got[k], ref[k]), k
