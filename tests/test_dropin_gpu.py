@@ -141,3 +141,37 @@ def test_search_batch_and_unsupported_env():
     with pytest.raises(TypeError):
         mcts.search(CartPoleEnv(np.zeros(4)))
     mcts.close()
+
+
+def test_raw_ctypes_binding_from_integration_md():
+    """The stand-alone ctypes stub shown in INTEGRATION.md section 3 (no alphazero_gym_b200 Python involved)."""
+    import ctypes as C
+    import os
+    cfg, g = G.load("pendulum_n25_k2")
+
+    class AzgConfig(C.Structure):
+        _fields_ = [(n, C.c_int32) for n in ("variant", "max_rollouts", "max_trees", "num_actions", "num_components",
+                                             "state_dim", "hidden", "n_hidden", "activation", "v_target", "puct_f32", "device")] + \
+                   [(n, C.c_double) for n in ("c_uct", "gamma", "epsilon", "c_pw", "kappa")] + \
+                   [(n, C.c_float) for n in ("action_bound", "log_std_min", "log_std_max")] + \
+                   [("flags", C.c_uint32), ("seed", C.c_uint64)]
+
+    root_dir = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = C.CDLL(os.path.join(root_dir, "alphazero_gym_b200", "lib", "libazg.so"))
+    lib.azg_last_error.restype = C.c_char_p
+    c = AzgConfig(1, 25, 1, 2, 2, 3, 128, 3, 1, 0, 1, 0, 0.05, 1.0, 0.0, 1.0, 0.5, 2.0, -5.0, 2.0, 0, 34)
+    eng = C.c_void_p()
+    assert lib.azg_create(C.byref(c), C.byref(eng)) == 0, lib.azg_last_error()
+    w = g["weights"].astype(np.float32)
+    assert lib.azg_set_weights(eng, w.ctypes.data_as(C.c_void_p), C.c_int64(w.size), None) == 0
+    cmax = lib.azg_cmax(eng)
+    root = np.ascontiguousarray(g["root_state"][:1], np.float64)
+    actions, counts = np.empty((1, cmax), np.float32), np.empty((1, cmax), np.int32)
+    Q, Vt, nc = np.empty((1, cmax)), np.empty(1), np.empty(1, np.int32)
+    rc = lib.azg_search_host(eng, 1, root.ctypes.data_as(C.c_void_p), None, 25, C.c_int64(0), actions.ctypes.data_as(C.c_void_p),
+                             counts.ctypes.data_as(C.c_void_p), Q.ctypes.data_as(C.c_void_p), Vt.ctypes.data_as(C.c_void_p),
+                             nc.ctypes.data_as(C.c_void_p))
+    assert rc == 0, lib.azg_last_error()
+    n = int(nc[0])
+    assert np.array_equal(counts[0, :n], g["counts"][0, :n]) and close(Q[0, :n], g["Q"][0, :n])
+    lib.azg_destroy(eng)
