@@ -25,7 +25,7 @@ def stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + [os.path.join(os.path.dirname(HERE), "include", "azg.h")]
+    deps = sources() + [os.path.join(os.path.dirname(HERE), "include", "azg.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(s) > t for s in deps)
 
 
