@@ -88,6 +88,36 @@ __device__ __forceinline__ float mlp_act(float v) {
     return (v != v) ? v : res;
 }
 
+// the same activation on a pair, with the FMA-pipe work packed into f32x2 instructions (each half is the scalar
+// IEEE operation, so results are bit-identical to mlp_act on each element)
+template <int ACT>
+__device__ __forceinline__ float2 mlp_act2(float2 v) {
+    if (ACT == 0) return make_float2(v.x > 0.0f ? v.x : 0.0f, v.y > 0.0f ? v.y : 0.0f);
+    const float2 xx = make_float2(fmaxf(v.x, -20.0f), fmaxf(v.y, -20.0f));
+    const float2 tn = __fmul2_rn(xx, make_float2(1.44269504088896341f, 1.44269504088896341f));
+    const float2 n = make_float2(rintf(tn.x), rintf(tn.y));
+    float2 r = __ffma2_rn(n, make_float2(-0.693359375f, -0.693359375f), xx);
+    r = __ffma2_rn(n, make_float2(2.12194440e-4f, 2.12194440e-4f), r);
+    float2 p = make_float2(1.9875691500E-4f, 1.9875691500E-4f);
+    p = __ffma2_rn(p, r, make_float2(1.3981999507E-3f, 1.3981999507E-3f));
+    p = __ffma2_rn(p, r, make_float2(8.3334519073E-3f, 8.3334519073E-3f));
+    p = __ffma2_rn(p, r, make_float2(4.1665795894E-2f, 4.1665795894E-2f));
+    p = __ffma2_rn(p, r, make_float2(1.6666665459E-1f, 1.6666665459E-1f));
+    p = __ffma2_rn(p, r, make_float2(5.0000001201E-1f, 5.0000001201E-1f));
+    const float2 z = __fmul2_rn(r, r);
+    const float2 pl = __ffma2_rn(p, z, r);
+    const float2 t = make_float2(__uint_as_float((uint32_t)((int32_t)n.x + 127) << 23), __uint_as_float((uint32_t)((int32_t)n.y + 127) << 23));
+    const float2 e = __ffma2_rn(pl, t, __fadd2_rn(t, make_float2(-1.0f, -1.0f)));
+    float2 res;
+    res.x = v.x < -17.5f ? -1.0f : e.x;
+    res.y = v.y < -17.5f ? -1.0f : e.y;
+    res.x = v.x > 0.0f ? v.x : res.x;
+    res.y = v.y > 0.0f ? v.y : res.y;
+    res.x = (v.x != v.x) ? v.x : res.x;
+    res.y = (v.y != v.y) ? v.y : res.y;
+    return res;
+}
+
 // post-processing of one row's raw head outputs (policies.py:275-297 softmax priors; :617-631 GMM params)
 __device__ __forceinline__ void softmax_seq(const float* l, int n, float* p) {
     float m = l[0];
@@ -173,10 +203,9 @@ __device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float* d0 = actg + (col0 + 2 * c) * TU + row0;
-        *reinterpret_cast<float4*>(d0) = make_float4(mlp_act<ACT>(acc[0][c].x), mlp_act<ACT>(acc[1][c].x),
-                                                     mlp_act<ACT>(acc[2][c].x), mlp_act<ACT>(acc[3][c].x));
-        *reinterpret_cast<float4*>(d0 + TU) = make_float4(mlp_act<ACT>(acc[0][c].y), mlp_act<ACT>(acc[1][c].y),
-                                                          mlp_act<ACT>(acc[2][c].y), mlp_act<ACT>(acc[3][c].y));
+        const float2 e0 = mlp_act2<ACT>(acc[0][c]), e1 = mlp_act2<ACT>(acc[1][c]), e2 = mlp_act2<ACT>(acc[2][c]), e3 = mlp_act2<ACT>(acc[3][c]);
+        *reinterpret_cast<float4*>(d0) = make_float4(e0.x, e1.x, e2.x, e3.x);
+        *reinterpret_cast<float4*>(d0 + TU) = make_float4(e0.y, e1.y, e2.y, e3.y);
     }
     group_sync(bar, MLP_GTHREADS(H));
 }
@@ -214,11 +243,14 @@ __device__ __forceinline__ void mlp_unit(const MlpParams& p, const float* w, flo
         const float* W0 = w;
         const float* b0 = w + S * H;
 #pragma unroll 4
-        for (int j = q * (H / NQ); j < (q + 1) * (H / NQ); ++j) {
-            float acc = b0[j];
+        for (int j = q * (H / NQ); j < (q + 1) * (H / NQ); j += 2) {
+            float2 acc = *reinterpret_cast<const float2*>(b0 + j);
 #pragma unroll
-            for (int s = 0; s < S; ++s) acc = __fmaf_rn(W0[s * H + j], x[s], acc);
-            actg[j * TU + row] = mlp_act<ACT>(acc);
+            for (int s = 0; s < S; ++s)
+                acc = __ffma2_rn(make_float2(x[s], x[s]), *reinterpret_cast<const float2*>(W0 + s * H + j), acc);
+            const float2 e = mlp_act2<ACT>(acc);
+            actg[j * TU + row] = e.x;
+            actg[(j + 1) * TU + row] = e.y;
         }
     }
     group_sync(bar, MLP_GTHREADS(H));
@@ -233,16 +265,17 @@ __device__ __forceinline__ void mlp_unit(const MlpParams& p, const float* w, flo
         const float* Wh = w + off;
         const float* bh = Wh + H * p.PO_PAD;
         for (int c = q; c < p.PO_PAD / 4; c += NQ) {
-            float4 acc = *reinterpret_cast<const float4*>(bh + c * 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(bh + c * 4);
+            float2 lo = make_float2(b4.x, b4.y), hi = make_float2(b4.z, b4.w);
 #pragma unroll 8
             for (int k = 0; k < H; ++k) {
                 const float a = actg[k * TU + row];
                 const float4 w4 = *reinterpret_cast<const float4*>(Wh + k * p.PO_PAD + c * 4);
-                acc.x = __fmaf_rn(w4.x, a, acc.x);
-                acc.y = __fmaf_rn(w4.y, a, acc.y);
-                acc.z = __fmaf_rn(w4.z, a, acc.z);
-                acc.w = __fmaf_rn(w4.w, a, acc.w);
+                const float2 av = make_float2(a, a);
+                lo = __ffma2_rn(av, make_float2(w4.x, w4.y), lo);
+                hi = __ffma2_rn(av, make_float2(w4.z, w4.w), hi);
             }
+            const float4 acc = make_float4(lo.x, lo.y, hi.x, hi.y);
             outg[(c * 4 + 0) * TU + row] = acc.x;
             outg[(c * 4 + 1) * TU + row] = acc.y;
             outg[(c * 4 + 2) * TU + row] = acc.z;
