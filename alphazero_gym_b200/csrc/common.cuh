@@ -7,7 +7,9 @@
 //     only: 64 B for the discrete tree (node + its A=2 edges) and 64 B for the continuous tree (sector 0:
 //     edge statistics + the child node it leads to -- edges and non-root nodes are 1:1, SURVEY 7-4;
 //     sector 1: that node's inline child list).  64 B is also the DRAM burst, so a row miss wastes nothing;
-//   * COLD structure-of-arrays side tables that select/backup never touch: env state, cached policy head.
+//   * the continuous tree adds a 64 B control block per tree (scalars, inline path, root child map) and a
+//     compact root edge table (the root's children statistics, 32 B each, contiguous);
+//   * COLD structure-of-arrays side tables that select/backup never touch: CartPole env state, cached policy head.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,27 +35,55 @@ static_assert(sizeof(DRow) == 64, "discrete row must be two 32 B sectors");
 #define DROW_NONE 0xFFFFu
 
 struct __align__(16) CRow {  // ActionContinuous + the NodeContinuous it leads to (states.py:194-289, :365-433)
-    // sector 0 -- read for every child scanned by UCT and rewritten by backup
+    // sector 0 ("hot" sector, struct CHot) -- read for every child scanned by UCT and rewritten by backup.
+    // For children of the ROOT this sector is not used: their hot sectors live contiguously in the root edge
+    // table (TreeParams::et), because the root is scanned in every simulation and has up to 16 children.
     double W;                // Action.W
     double r;                // child Node.r (already / PENDULUM_R_SCALE)
     float V;                 // child Node.V
     float action;            // Action.action
     int32_t n_e;             // Action.n
     uint32_t nn_flags;       // child Node.n in bits 0..23 | CROW_EXPANDED | CROW_TERMINAL
-    // sector 1 -- the child node's own child_actions list, in insertion order; read only when the
-    // descent enters this node, appended to by progressive widening
-    uint8_t kids[31];        // row indices
+    // sector 1 -- the child node's own child_actions list (insertion order) and its hidden env state; read
+    // only when the descent enters this node, appended to by progressive widening
+    uint8_t kids[15];        // row indices
     uint8_t nkids;
+    double th, thdot;        // Pendulum hidden state of the node
 };
 static_assert(sizeof(CRow) == 64, "continuous row must be two 32 B sectors (one 64 B DRAM burst)");
-#define CROW_MAX_KIDS 31
+#define CROW_MAX_KIDS 15
+#define CROOT_MAX_KIDS 16
 #define ROW_TERMINAL 1u
 #define CROW_NMASK 0x00FFFFFFu
 #define CROW_EXPANDED 0x01000000u
 #define CROW_TERMINAL 0x02000000u
 
+struct __align__(16) CHot {  // sector 0 of a CRow / one entry of the root edge table
+    double W, r;
+    float V, action;
+    int32_t n_e;
+    uint32_t nn_flags;
+};
+static_assert(sizeof(CHot) == 32, "hot sector");
+
+struct __align__(16) CCtl {  // per-tree control block: everything a simulation needs besides rows, in ONE 64 B line
+    uint8_t n_rows, depth, root_nk, j0;  // rows in use, recorded path length, root children, root-edge index of path[0]
+    int32_t draws;           // selection RNG draw counter (stream 0)
+    int32_t leaf;            // LEAF_* word for the evaluation kernel
+    int32_t root_nn;         // root Node.n
+    float root_V;            // root Node.V
+    uint16_t pw;             // progressive-widening insert counter (stream 1 index)
+    uint16_t pad;
+    double leafR;            // return at the leaf edge of the current simulation: r + gamma*V
+    uint8_t path[16];        // rows visited by the current simulation (deeper levels spill to TreeParams::path)
+    uint8_t root_kids[16];   // row index of root child j (insertion order)
+};
+static_assert(sizeof(CCtl) == 64, "control block must be one 64 B line");
+
 // leaf word handed from the tree kernels to the evaluation kernel
 #define LEAF_ROW_MASK 0xFFFF
+#define LEAF_J_SHIFT 16              // continuous: index of the leaf in the root edge table ...
+#define LEAF_ROOTCHILD (1 << 28)     // ... valid when the leaf is a child of the root
 #define LEAF_EVAL (1 << 29)      // the leaf is new: evaluate it
 #define LEAF_TERMINAL (1 << 30)  // V is forced to 0
 
@@ -72,17 +102,16 @@ struct TreeParams {
     double* dstate;   // [B][R][4]
     // continuous tables
     CRow* crows;      // [B][R]
-    double2* cstate;  // [B][R]   (th, thdot)
     float* chead;     // [B][R][HS]  mu[K], sigma[K], prob[K]
-    double* leafR;    // [B] return at the leaf edge of the current simulation: r + gamma*V (continuous)
+    CHot* et;         // [B][16]  root edge table: hot sectors of the root's children, insertion order
+    CCtl* ctl;        // [B]      control blocks
     const int32_t* pw_table;  // [max_rollouts + 2]  ceil(c_pw * (n+1)^kappa), built on the host
     // per-tree scalars
+    // per-tree scalars of the discrete tree (the continuous tree keeps them in CCtl)
     int32_t* n_rows;  // rows / nodes in use
     int32_t* draws;   // selection RNG draw counter (stream 0)
-    int32_t* pw;      // progressive-widening insert counter (stream 1 index)
-    int32_t* depth;   // length of the recorded path
     int32_t* leaf;    // LEAF_* word
-    uint8_t* path;    // [B][R] rows visited by the current simulation (continuous)
+    uint8_t* path;    // [B][R] continuous: path entries beyond the 16 held in CCtl
     uint32_t* ctr;    // [4][B]: levels, children scanned, terminal-leaf sims, evals
     float4* X;        // [B] network input of the leaf
     const double* root_state;

@@ -45,10 +45,10 @@ struct azg_engine {
     DRow* drows = nullptr;
     double* dstate = nullptr;
     CRow* crows = nullptr;
-    double2* cstate = nullptr;
+    CHot* et = nullptr;
+    CCtl* ctl = nullptr;
     float* chead = nullptr;
-    double* leafR = nullptr;
-    int32_t *pw_table = nullptr, *n_rows = nullptr, *draws = nullptr, *pw = nullptr, *depth = nullptr, *leaf = nullptr;
+    int32_t *pw_table = nullptr, *n_rows = nullptr, *draws = nullptr, *leaf = nullptr;
     uint8_t* path = nullptr;
     uint32_t* ctr = nullptr;
     float4* X = nullptr;
@@ -95,8 +95,8 @@ extern "C" void azg_destroy(azg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
-    void* ptrs[] = {e->drows, e->dstate, e->crows, e->cstate, e->chead, e->leafR, e->pw_table, e->n_rows, e->draws, e->pw,
-                    e->depth, e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->r_actions,
+    void* ptrs[] = {e->drows, e->dstate, e->crows, e->et, e->ctl, e->chead, e->pw_table, e->n_rows, e->draws,
+                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -121,7 +121,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     } else {
         if (c.state_dim != 3) return fail(AZG_EINVAL, "continuous variant is Pendulum: state_dim must be 3");
         if (c.num_components < 1 || c.num_components > AZG_MAX_K) return fail(AZG_EINVAL, "num_components must be in 1..8");
-        if (c.max_rollouts + 2 > 255) return fail(AZG_EINVAL, "continuous variant supports n_rollouts <= 253 (byte parent links)");
+        if (c.max_rollouts + 2 > 255) return fail(AZG_EINVAL, "continuous variant supports n_rollouts <= 253 (8-bit row links)");
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -158,9 +158,9 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
             if (n <= c.max_rollouts) cm = std::max(cm, pwt.back());
         }
         e->cmax = cm + 1;
-        if (cm + 1 > CROW_MAX_KIDS) {
+        if (cm > CROW_MAX_KIDS) {
             delete e;
-            return fail(AZG_ECAPACITY, "progressive-widening fan-out exceeds the 31 inline child slots of a row (c_pw/kappa/n_rollouts too large)");
+            return fail(AZG_ECAPACITY, "progressive-widening fan-out exceeds the 15 inline child slots of a row (c_pw/kappa/n_rollouts too large)");
         }
     } else {
         e->cmax = c.num_actions;
@@ -179,15 +179,15 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
         ALLOC(dstate, B * R * 4);
     } else {
         ALLOC(crows, B * R);
-        ALLOC(cstate, B * R);
+        ALLOC(et, B * CROOT_MAX_KIDS);
+        ALLOC(ctl, B);
         ALLOC(chead, B * R * e->HS);
-        ALLOC(leafR, B);
         ALLOC(pw_table, pwt.size());
         ALLOC(path, B * R);
         CK(cudaMemcpy(e->pw_table, pwt.data(), pwt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CK(cudaMemset(e->chead, 0, B * R * e->HS * sizeof(float)));
     }
-    ALLOC(n_rows, B); ALLOC(draws, B); ALLOC(pw, B); ALLOC(depth, B); ALLOC(leaf, B);
+    ALLOC(n_rows, B); ALLOC(draws, B); ALLOC(leaf, B);
     ALLOC(ctr, 4 * B);
     ALLOC(X, B);
     ALLOC(root_state, B * 4);
@@ -293,9 +293,9 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.gamma_f32 = (float)c.gamma; p.action_bound = c.action_bound;
     p.seed = c.seed; p.tree_id0 = tree_id0;
     p.drows = e->drows; p.dstate = e->dstate;
-    p.crows = e->crows; p.cstate = e->cstate; p.chead = e->chead; p.leafR = e->leafR;
+    p.crows = e->crows; p.et = e->et; p.ctl = e->ctl; p.chead = e->chead;
     p.pw_table = e->pw_table;
-    p.n_rows = e->n_rows; p.draws = e->draws; p.pw = e->pw; p.depth = e->depth; p.leaf = e->leaf; p.path = e->path;
+    p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path;
     p.ctr = e->ctr; p.X = e->X; p.root_state = e->root_state; p.root_n_init = e->root_n_init; p.err = e->err;
     p.tapeV = e->tapeV; p.tapeP = e->tapeP; p.tapeA = e->tapeA;
     return p;
@@ -310,7 +310,7 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     m.variant = c.variant; m.A = c.num_actions; m.K = c.num_components; m.R = e->R; m.HS = e->HS;
     m.ls_min = c.log_std_min; m.ls_max = c.log_std_max;
     m.leaf = e->leaf; m.drows = e->drows; m.crows = e->crows; m.chead = e->chead; m.evals = e->ctr + (size_t)3 * n;
-    m.leafR = e->leafR; m.gamma_f32 = (float)c.gamma;
+    m.ctl = e->ctl; m.et = e->et; m.gamma_f32 = (float)c.gamma;
     m.head_dim = azg_head_dim(e);
     return m;
 }
@@ -586,13 +586,18 @@ extern "C" int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]) {
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaDeviceSynchronize());
     std::vector<uint32_t> c(4 * (size_t)B);
-    std::vector<int32_t> dr(B), pw(B);
+    std::vector<int32_t> dr(B, 0), pw(B, 0);
     // counters are laid out [4][B_of_the_search]; the search that wrote them used last_B
     const int LB = e->last_B > 0 ? e->last_B : B;
     std::vector<uint32_t> all(4 * (size_t)LB);
     CK(cudaMemcpy(all.data(), e->ctr, all.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(dr.data(), e->draws, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(pw.data(), e->pw, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (e->cfg.variant == AZG_DISCRETE) {
+        CK(cudaMemcpy(dr.data(), e->draws, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    } else {
+        std::vector<CCtl> cc(B);
+        CK(cudaMemcpy(cc.data(), e->ctl, (size_t)B * sizeof(CCtl), cudaMemcpyDeviceToHost));
+        for (int t = 0; t < B; ++t) { dr[t] = cc[t].draws; pw[t] = cc[t].pw; }
+    }
     for (int k = 0; k < 8; ++k) out[k] = 0;
     const int nb = std::min(B, LB);
     for (int t = 0; t < nb; ++t) {
@@ -654,40 +659,47 @@ extern "C" int azg_dump_tree_continuous(azg_engine* e, int32_t B, const azg_dump
     CK(cudaDeviceSynchronize());
     const size_t R = e->R, K3 = e->K3, HS = e->HS;
     std::vector<CRow> rows((size_t)B * R);
-    std::vector<double2> st((size_t)B * R);
+    std::vector<CHot> et((size_t)B * CROOT_MAX_KIDS);
+    std::vector<CCtl> ctl(B);
     std::vector<float> hd((size_t)B * R * HS);
-    std::vector<int32_t> nr(B);
     CK(cudaMemcpy(rows.data(), e->crows, rows.size() * sizeof(CRow), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(st.data(), e->cstate, st.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(et.data(), e->et, et.size() * sizeof(CHot), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(ctl.data(), e->ctl, ctl.size() * sizeof(CCtl), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(hd.data(), e->chead, hd.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(nr.data(), e->n_rows, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
     std::vector<int32_t> par(R);
+    std::vector<const CHot*> hot(R);
     for (size_t t = 0; t < (size_t)B; ++t) {
-        o->n_rows[t] = nr[t];
-        // parent links are implicit in the inline child lists
-        for (size_t i = 0; i < R; ++i) par[i] = -1;
-        for (size_t i = 0; i < R && (int)i < nr[t]; ++i) {
+        const int nr = ctl[t].n_rows;
+        o->n_rows[t] = nr;
+        // parent links are implicit in the child lists; root children keep their statistics in the edge table
+        for (size_t i = 0; i < R; ++i) { par[i] = -1; hot[i] = reinterpret_cast<const CHot*>(&rows[t * R + i]); }
+        for (int k = 0; k < ctl[t].root_nk && k < CROOT_MAX_KIDS; ++k) {
+            const size_t kid = ctl[t].root_kids[k];
+            if (kid < R) { par[kid] = 0; hot[kid] = &et[t * CROOT_MAX_KIDS + k]; }
+        }
+        for (size_t i = 1; i < R && (int)i < nr; ++i) {
+            if (!(hot[i]->nn_flags & CROW_EXPANDED)) continue;
             const CRow& r = rows[t * R + i];
-            if (!(r.nn_flags & CROW_EXPANDED)) continue;
             for (int k = 0; k < r.nkids && k < CROW_MAX_KIDS; ++k)
                 if (r.kids[k] < R) par[r.kids[k]] = (int32_t)i;
         }
         for (size_t i = 0; i < R; ++i) {
             const size_t q = t * R + i;
-            const bool live = (int)i < nr[t];
+            const bool live = (int)i < nr;
+            const CHot& h = *hot[i];
             const CRow& r = rows[q];
-            const bool ex = live && (r.nn_flags & CROW_EXPANDED);
+            const bool ex = live && (h.nn_flags & CROW_EXPANDED);
             o->parent[q] = live ? par[i] : 0;
-            o->action[q] = live && i > 0 ? r.action : 0.0f;
-            o->eW[q] = live ? r.W : 0.0;
-            o->en[q] = live ? r.n_e : 0;
+            o->action[q] = live && i > 0 ? h.action : 0.0f;
+            o->eW[q] = live ? h.W : 0.0;
+            o->en[q] = live ? h.n_e : 0;
             o->expanded[q] = ex ? 1 : 0;
-            o->node_n[q] = ex ? (int32_t)(r.nn_flags & CROW_NMASK) : 0;
-            o->terminal[q] = ex && (r.nn_flags & CROW_TERMINAL) ? 1 : 0;
-            o->V[q] = ex ? r.V : 0.0f;
-            o->r[q] = ex ? r.r : 0.0;
-            o->state[q * 2] = ex ? st[q].x : 0.0;
-            o->state[q * 2 + 1] = ex ? st[q].y : 0.0;
+            o->node_n[q] = ex ? (i == 0 ? ctl[t].root_nn : (int32_t)(h.nn_flags & CROW_NMASK)) : 0;
+            o->terminal[q] = ex && (h.nn_flags & CROW_TERMINAL) ? 1 : 0;
+            o->V[q] = ex ? h.V : 0.0f;
+            o->r[q] = ex ? h.r : 0.0;
+            o->state[q * 2] = ex ? r.th : 0.0;
+            o->state[q * 2 + 1] = ex ? r.thdot : 0.0;
             for (size_t k = 0; k < K3; ++k) o->head[q * K3 + k] = ex ? hd[q * HS + k] : 0.0f;
         }
     }

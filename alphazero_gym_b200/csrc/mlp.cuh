@@ -40,7 +40,8 @@ struct MlpParams {
     CRow* crows;
     float* chead;
     uint32_t* evals;     // per-tree evaluation counter
-    double* leafR;       // continuous: leafR[t] += gamma_f32 * V  (first backup step, mcts.py:260-263)
+    CCtl* ctl;           // continuous: leaf word; ctl[t].leafR += gamma_f32 * V  (first backup step, mcts.py:260-263)
+    CHot* et;            // continuous: root edge table (V of a root child is written there)
     float gamma_f32;
     float* outV;
     float* outHead;
@@ -219,12 +220,18 @@ __device__ __forceinline__ void mlp_unit(const MlpParams& p, const float* w, flo
     const int gr = row0 + row;
     int leafw = 0;
     bool need = gr < p.n;
+    double lr = 0.0;
     if (need && p.mode == 0) {
-        leafw = p.leaf[gr];
+        if (p.variant == 1) {  // continuous: leaf word and leafR share the first 32 B of the control block
+            const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
+            const uint4 c0 = cp[0], c1 = cp[1];
+            leafw = (int)c0.z;
+            lr = __hiloint2double((int)c1.w, (int)c1.z);
+        } else {
+            leafw = p.leaf[gr];
+        }
         need = (leafw & LEAF_EVAL) != 0;
     }
-    double lr = 0.0;
-    if (need && p.mode == 0 && p.variant == 1 && q == 0) lr = p.leafR[gr];  // in flight during the whole unit
     // ---- layer 0: S -> H, NQ threads per row, H/NQ outputs each
     {
         float x[S];
@@ -318,8 +325,9 @@ __device__ __forceinline__ void mlp_unit(const MlpParams& p, const float* w, flo
                 d->V = V;
                 *reinterpret_cast<float2*>(d->prior) = make_float2(post[0], post[1]);
             } else {
-                p.crows[ri].V = V;
-                p.leafR[gr] = lr + (double)__fmul_rn(p.gamma_f32, V);
+                if (leafw & LEAF_ROOTCHILD) p.et[(size_t)gr * CROOT_MAX_KIDS + ((leafw >> LEAF_J_SHIFT) & 0xFF)].V = V;
+                else p.crows[ri].V = V;
+                p.ctl[gr].leafR = lr + (double)__fmul_rn(p.gamma_f32, V);
                 float* h = p.chead + ri * p.HS;
                 for (int i = 0; i < npost; ++i) h[i] = post[i];
             }

@@ -12,41 +12,73 @@
 // same work costs ~1/10 of the issue slots, the f64 env step / Box-Muller run on full warps with no
 // barriers, and memory-level parallelism comes from 65536 independent threads instead of from lanes.
 //
-// Per level the thread holds the node's inline child list (sector 1 of its row, 2 x LDG.128), gathers the
-// children's statistics sectors four at a time (independent LDG.128 pairs in flight), evaluates UCT in
-// f64 in the reference's expression order and keeps (max, bit-set of winners) for the random tie-break.
+// Memory traffic is what bounds this kernel (profiles/r1b: 128 MB of DRAM traffic per launch against 19 MB
+// algorithmic), so the layout is built around 64 B DRAM bursts:
+//   * one 64 B control block per tree (CCtl) carries every scalar, the recorded path and the root's child map;
+//   * the root is scanned in every simulation and has the widest fan-out, so the statistics sectors of its
+//     children sit contiguously in the root edge table (2 children per 64 B burst instead of 1);
+//   * a node's hidden env state rides in the second sector of its row together with its child list, so
+//     entering a node and expanding below it cost no extra line.
 #pragma once
 #include "common.cuh"
 #include "env.cuh"
 
-struct CHot {  // sector 0 of a CRow
-    double W, r;
-    float V, action;
-    int32_t n_e;
-    uint32_t nn_flags;
-};
-
-__device__ __forceinline__ CHot load_hot(const CRow* p) {
+__device__ __forceinline__ CHot load_hot(const void* p) {
     CHot h;
     const uint4* s = reinterpret_cast<const uint4*>(p);
     uint4* d = reinterpret_cast<uint4*>(&h);
     d[0] = s[0]; d[1] = s[1];
     return h;
 }
-__device__ __forceinline__ void load_kids(const CRow* p, uint32_t kw[8]) {
-    const uint4* s = reinterpret_cast<const uint4*>(p);
-    const uint4 a = s[2], b = s[3];
-    kw[0] = a.x; kw[1] = a.y; kw[2] = a.z; kw[3] = a.w;
-    kw[4] = b.x; kw[5] = b.y; kw[6] = b.z; kw[7] = b.w;
-}
-__device__ __forceinline__ void store_new_row(CRow* p, double r, float V, float action, uint32_t nn_flags) {
-    CHot h;
-    h.W = 0.0; h.r = r; h.V = V; h.action = action; h.n_e = 0; h.nn_flags = nn_flags;
+__device__ __forceinline__ void store_hot(void* p, const CHot& h) {
     const uint4* s = reinterpret_cast<const uint4*>(&h);
     uint4* d = reinterpret_cast<uint4*>(p);
     d[0] = s[0]; d[1] = s[1];
-    d[2] = make_uint4(0, 0, 0, 0);
-    d[3] = make_uint4(0, 0, 0, 0);
+}
+struct CSec1 {  // sector 1 of a CRow
+    uint32_t kw[4];  // kids[15] + nkids in the top byte of kw[3]
+    double th, thdot;
+};
+__device__ __forceinline__ CSec1 load_sec1(const CRow* p) {
+    CSec1 s;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    const uint4 a = q[2], b = q[3];
+    s.kw[0] = a.x; s.kw[1] = a.y; s.kw[2] = a.z; s.kw[3] = a.w;
+    s.th = __hiloint2double((int)b.y, (int)b.x);
+    s.thdot = __hiloint2double((int)b.w, (int)b.z);
+    return s;
+}
+__device__ __forceinline__ void store_sec1_new(CRow* p, double th, double thdot) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[2] = make_uint4(0, 0, 0, 0);
+    q[3] = make_uint4((uint32_t)__double2loint(th), (uint32_t)__double2hiint(th), (uint32_t)__double2loint(thdot),
+                      (uint32_t)__double2hiint(thdot));
+}
+__device__ __forceinline__ CCtl load_ctl(const CCtl* p) {
+    CCtl c;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&c);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+    return c;
+}
+__device__ __forceinline__ void store_ctl(CCtl* p, const CCtl& c) {
+    const uint4* s = reinterpret_cast<const uint4*>(&c);
+    uint4* d = reinterpret_cast<uint4*>(p);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+// byte j of a 16-byte list held in four registers, without dynamic register indexing
+__device__ __forceinline__ int list_byte(const uint32_t w[4], int j) {
+    uint32_t v = w[0];
+    v = (j >> 2) == 1 ? w[1] : v;
+    v = (j >> 2) == 2 ? w[2] : v;
+    v = (j >> 2) == 3 ? w[3] : v;
+    return (int)((v >> (8 * (j & 3))) & 0xFFu);
+}
+__device__ __forceinline__ void set_list_byte(uint32_t w[4], int j, int val) {
+    const uint32_t m = 0xFFu << (8 * (j & 3)), b = (uint32_t)val << (8 * (j & 3));
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if ((j >> 2) == i) w[i] = (w[i] & ~m) | b;
 }
 
 // stream 1: noise of the j-th widening insert of `tree`: component uniform + K standard normals
@@ -86,20 +118,26 @@ __device__ __forceinline__ float new_action(const TreeParams& p, int t, int node
     return sample_action(p, p.chead + ((size_t)t * p.R + node) * p.HS, u, z);
 }
 
+__device__ __forceinline__ CHot fresh_hot(double r, float V, float action, uint32_t nn_flags) {
+    CHot h;
+    h.W = 0.0; h.r = r; h.V = V; h.action = action; h.n_e = 0; h.nn_flags = nn_flags;
+    return h;
+}
+
 // MCTSContinuous.initialize_search (mcts.py:589-600): new root row, network input = obs(root)
 __global__ void k_init_continuous(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.B) return;
     const double th = p.root_state[(size_t)t * 2], thdot = p.root_state[(size_t)t * 2 + 1];
-    store_new_row(p.crows + (size_t)t * p.R, 0.0, p.use_tape ? p.tapeV[(size_t)t * p.R] : 0.0f, 0.0f, CROW_EXPANDED);
-    p.cstate[(size_t)t * p.R] = make_double2(th, thdot);
+    CRow* root = p.crows + (size_t)t * p.R;
+    store_hot(root, fresh_hot(0.0, p.use_tape ? p.tapeV[(size_t)t * p.R] : 0.0f, 0.0f, CROW_EXPANDED));
+    store_sec1_new(root, th, thdot);
     p.X[t] = env::pendulum_obs(th, thdot);
-    p.leaf[t] = 0 | LEAF_EVAL;
-    p.leafR[t] = 0.0;
-    p.n_rows[t] = 1;
-    p.draws[t] = 0;
-    p.pw[t] = 0;
-    p.depth[t] = 0;
+    CCtl c;
+    memset(&c, 0, sizeof c);
+    c.n_rows = 1;
+    c.leaf = 0 | LEAF_EVAL;
+    store_ctl(p.ctl + t, c);
     for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
 }
 
@@ -108,12 +146,18 @@ __global__ void k_root_insert_continuous(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.B) return;
     CRow* rows = p.crows + (size_t)t * p.R;
+    CCtl c = load_ctl(p.ctl + t);
     const float a = new_action(p, t, 0, 1, 0);
-    store_new_row(rows + 1, 0.0, 0.0f, a, 0);
-    rows[0].kids[0] = 1;
-    rows[0].nkids = 1;
-    p.n_rows[t] = 2;
-    p.pw[t] = 1;
+    store_hot(p.et + (size_t)t * CROOT_MAX_KIDS, fresh_hot(0.0, 0.0f, a, 0));
+    store_hot(rows + 1, fresh_hot(0.0, 0.0f, a, 0));  // unused mirror of the edge-table entry (keeps the row defined)
+    store_sec1_new(rows + 1, 0.0, 0.0);
+    c.root_kids[0] = 1;
+    c.root_nk = 1;
+    c.n_rows = 2;
+    c.pw = 1;
+    c.root_V = rows[0].V;  // written by the root evaluation
+    c.root_nn = 0;
+    store_ctl(p.ctl + t, c);
 }
 
 #define KIND_INSERT 0    // progressive widening: create a new edge below `cur`, then its node
@@ -121,150 +165,179 @@ __global__ void k_root_insert_continuous(const TreeParams p) {
 #define KIND_TERMINAL 2  // the trace ended on an existing terminal node
 #define KIND_ERROR 3
 
+// UCT over up to 16 children whose hot sectors are gathered through `hot_of(j)`; returns the selected index
+// (mcts.py:729-741 + helpers.argmax + epsilon_greedy)
+template <typename HotOf>
+__device__ __forceinline__ int uct_select(const TreeParams& p, int64_t tree, int nk, uint32_t cur_nn, float cur_V, int& draws, bool& nan,
+                                          HotOf hot_of) {
+    const double sq = sqrt((double)(cur_nn + 1));
+    double best = -CUDART_INF;
+    uint32_t win = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        if (w * 4 < nk) {
+            CHot c[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[i] = hot_of(w * 4 + i < nk ? w * 4 + i : 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = w * 4 + i;
+                if (j < nk) {
+                    const int n = c[i].n_e;
+                    const double Q = n > 0 ? c[i].W / (double)n : (double)cur_V;
+                    const double u = Q + p.c_uct * (sq / (double)(n + 1));  // mcts.py:731-732
+                    nan |= (u != u);
+                    if (u > best) { best = u; win = 1u << j; }
+                    else if (u == best) win |= 1u << j;
+                }
+            }
+        }
+    }
+    bool random_pick = false;
+    if (p.epsilon != 0) {  // epsilon_greedy (mcts.py:175-195)
+        const double x = (double)u32_to_unit(rng_select_u32(p, tree, draws++));
+        random_pick = x < p.epsilon;
+    }
+    if (random_pick) return u32_to_index(rng_select_u32(p, tree, draws++), nk);
+    // random.choice(winners): the draw is consumed even when there is a single winner
+    const int nw = __popc(win);
+    const int pick = nw > 1 ? u32_to_index(rng_select_u32(p, tree, draws), nw) : 0;
+    ++draws;
+    return nw > 0 ? (int)__fns(win, 0, pick + 1) : 0;
+}
+
 template <bool BACKUP, bool SELECT>
 __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.B) return;
     CRow* rows = p.crows + (size_t)t * p.R;
-    uint8_t* path = p.path + (size_t)t * p.R;
+    CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
+    uint8_t* path_ovf = p.path + (size_t)t * p.R;
+    CCtl c = load_ctl(p.ctl + t);
+    uint32_t pathw[4];
+    memcpy(pathw, c.path, 16);
 
     if (BACKUP) {
         // backprop (mcts.py:241-267) along the recorded path.  leafR already holds r_leaf + gamma*V_leaf
         // (the f32 product of NEP 50, added by the evaluation kernel's epilogue).
-        const int d = p.depth[t];
-        double Rv = p.leafR[t];
+        const int d = c.depth;
+        double Rv = c.leafR;
         for (int i = d - 1; i >= 0; --i) {
-            CRow* row = rows + path[i];
-            const CHot h = load_hot(row);
+            void* hp = i == 0 ? (void*)(et + c.j0) : (void*)(rows + (i < 16 ? list_byte(pathw, i) : (int)path_ovf[i]));
+            const CHot h = load_hot(hp);
             if (i != d - 1) Rv = h.r + p.gamma * Rv;
-            row->W = h.W + Rv;                                                      // Action.update (states.py:97-112)
-            *reinterpret_cast<int2*>(&row->n_e) = make_int2(h.n_e + 1, (int)(h.nn_flags + (i < d - 1 ? 1u : 0u)));
+            reinterpret_cast<CHot*>(hp)->W = h.W + Rv;  // Action.update (states.py:97-112)
+            *reinterpret_cast<int2*>(&reinterpret_cast<CHot*>(hp)->n_e) = make_int2(h.n_e + 1, (int)(h.nn_flags + (i < d - 1 ? 1u : 0u)));
         }
-        if (d > 0) rows[0].nn_flags += 1;  // root.n
+        if (d > 0) c.root_nn += 1;  // root.n
     }
 
     if (SELECT) {
         const int64_t tree = p.tree_id0 + t;
-        int draws = p.draws[t], n_rows = p.n_rows[t], pwc = p.pw[t];
-        int cur = 0, sel = -1, kind = KIND_ERROR, depth = 0;
-        uint32_t kw[8];
-        load_kids(rows, kw);
-        const CHot root = load_hot(rows);
-        uint32_t cur_nn = root.nn_flags & CROW_NMASK;
-        float cur_V = root.V;
-        int nk = kw[7] >> 24;
-        float sel_action = 0.0f;
-        double leaf_r = 0.0;
+        int draws = c.draws, n_rows = c.n_rows, pwc = c.pw;
+        int cur = 0, sel = -1, kind = KIND_ERROR, depth = 0, nk = c.root_nk;
+        uint32_t cur_nn = (uint32_t)c.root_nn;
+        float cur_V = c.root_V, sel_action = 0.0f;
+        double leaf_r = 0.0, cur_th = 0.0, cur_thdot = 0.0;
+        uint32_t kw[4], rootk[4];
+        memcpy(rootk, c.root_kids, 16);
+        kw[0] = rootk[0]; kw[1] = rootk[1]; kw[2] = rootk[2]; kw[3] = rootk[3];
         uint32_t levels = 0, scanned = 0;
         bool nan = false;
+        int jsel = 0;
         while (true) {
             ++levels;
             if (p.pw_table[cur_nn] - nk > 0) { kind = KIND_INSERT; break; }  // states.py:252-275
-            // UCT_j = Q_j + c_uct*(sqrt(node.n+1)/(n_j+1))   (mcts.py:731-732), children in insertion order
-            const double sq = sqrt((double)(cur_nn + 1));
-            double best = -CUDART_INF;
-            uint32_t win = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                if (w * 4 < nk) {
-                    CHot c[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int j = w * 4 + i;
-                        const int kid = j < nk ? (int)((kw[w] >> (8 * i)) & 0xFFu) : 0;
-                        c[i] = load_hot(rows + kid);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int j = w * 4 + i;
-                        if (j < nk) {
-                            const int n = c[i].n_e;
-                            const double Q = n > 0 ? c[i].W / (double)n : (double)cur_V;
-                            const double u = Q + p.c_uct * (sq / (double)(n + 1));
-                            nan |= (u != u);
-                            if (u > best) { best = u; win = 1u << j; }
-                            else if (u == best) win |= 1u << j;
-                        }
-                    }
-                }
+            CHot sh;
+            if (cur == 0) {
+                jsel = uct_select(p, tree, nk, cur_nn, cur_V, draws, nan, [&](int j) { return load_hot(et + j); });
+                sh = load_hot(et + jsel);
+            } else {
+                jsel = uct_select(p, tree, nk, cur_nn, cur_V, draws, nan, [&](int j) { return load_hot(rows + list_byte(kw, j)); });
+                sh = load_hot(rows + list_byte(kw, jsel));
             }
             scanned += nk;
-            int j;
-            bool random_pick = false;
-            if (p.epsilon != 0) {  // epsilon_greedy (mcts.py:175-195)
-                const double x = (double)u32_to_unit(rng_select_u32(p, tree, draws++));
-                random_pick = x < p.epsilon;
-            }
-            if (random_pick) {
-                j = u32_to_index(rng_select_u32(p, tree, draws++), nk);
-            } else {
-                // random.choice(winners): the draw is consumed even when there is a single winner
-                const int nw = __popc(win);
-                const int pick = nw > 1 ? u32_to_index(rng_select_u32(p, tree, draws), nw) : 0;
-                ++draws;
-                j = nw > 0 ? (int)__fns(win, 0, pick + 1) : 0;
-            }
-            sel = 0;
-#pragma unroll
-            for (int w = 0; w < 8; ++w)
-                if ((j >> 2) == w) sel = (int)((kw[w] >> (8 * (j & 3))) & 0xFFu);
-            const CHot sh = load_hot(rows + sel);
-            path[depth++] = (uint8_t)sel;
+            sel = list_byte(kw, jsel);
+            if (depth == 0) c.j0 = (uint8_t)jsel;
+            if (depth < 16) set_list_byte(pathw, depth, sel); else path_ovf[depth] = (uint8_t)sel;
+            ++depth;
             if (!(sh.nn_flags & CROW_EXPANDED)) { kind = KIND_EXPAND; sel_action = sh.action; break; }
+            const bool from_root = cur == 0;
             cur = sel;
             cur_nn = sh.nn_flags & CROW_NMASK;
             cur_V = sh.V;
-            if (sh.nn_flags & CROW_TERMINAL) { kind = KIND_TERMINAL; leaf_r = sh.r; break; }
-            load_kids(rows + cur, kw);
-            nk = kw[7] >> 24;
+            if (sh.nn_flags & CROW_TERMINAL) { kind = KIND_TERMINAL; leaf_r = sh.r; (void)from_root; break; }
+            const CSec1 s1 = load_sec1(rows + cur);
+            kw[0] = s1.kw[0]; kw[1] = s1.kw[1]; kw[2] = s1.kw[2]; kw[3] = s1.kw[3];
+            nk = (int)(kw[3] >> 24);
+            cur_th = s1.th; cur_thdot = s1.thdot;
         }
         if (nan) { atomicOr(p.err, ERR_NAN); kind = KIND_ERROR; }
-        if (kind == KIND_INSERT && (n_rows >= p.R || nk >= CROW_MAX_KIDS)) { atomicOr(p.err, ERR_CAPACITY); kind = KIND_ERROR; }
+        if (kind == KIND_INSERT && (n_rows >= p.R || n_rows >= 255 || nk >= (cur == 0 ? CROOT_MAX_KIDS : CROW_MAX_KIDS))) {
+            atomicOr(p.err, ERR_CAPACITY);
+            kind = KIND_ERROR;
+        }
 
         // ---- expansion: all lanes are reconverged here, so the f64 work below runs on full warps ----
+        const bool parent_is_root = cur == 0;  // (for KIND_EXPAND / KIND_INSERT `cur` is the parent of `sel`)
         if (kind == KIND_INSERT) {
             // add_pw_action (mcts.py:625-654): the new edge is selected immediately (mcts.py:725-727)
             sel = n_rows++;
             sel_action = new_action(p, t, cur, sel, pwc++);
-            rows[cur].kids[nk] = (uint8_t)sel;
-            rows[cur].nkids = (uint8_t)(nk + 1);
-            path[depth++] = (uint8_t)sel;
+            jsel = nk;
+            if (parent_is_root) {
+                set_list_byte(rootk, nk, sel);
+                c.root_nk = (uint8_t)(nk + 1);
+            } else {
+                rows[cur].kids[nk] = (uint8_t)sel;
+                rows[cur].nkids = (uint8_t)(nk + 1);
+            }
+            if (depth == 0) c.j0 = (uint8_t)jsel;
+            if (depth < 16) set_list_byte(pathw, depth, sel); else path_ovf[depth] = (uint8_t)sel;
+            ++depth;
         }
         if (kind == KIND_INSERT || kind == KIND_EXPAND) {
-            const double2 s = p.cstate[(size_t)t * p.R + cur];
+            if (parent_is_root) {  // the root's state sits in row 0 (read only when the tree grows at the root)
+                const CSec1 s0 = load_sec1(rows);
+                cur_th = s0.th; cur_thdot = s0.thdot;
+            }
             double nth, nthdot, rew;
-            const bool term = env::pendulum_step(s.x, s.y, sel_action, nth, nthdot, rew);
+            const bool term = env::pendulum_step(cur_th, cur_thdot, sel_action, nth, nthdot, rew);
             const double r = rew / AZG_PENDULUM_R_SCALE;  // mcts.py:687
             const uint32_t fl = CROW_EXPANDED | (term ? CROW_TERMINAL : 0u);
             float V = 0.0f;
             if (p.use_tape && !term) V = p.tapeV[(size_t)t * p.R + sel];
+            void* hp = parent_is_root ? (void*)(et + jsel) : (void*)(rows + sel);
             if (kind == KIND_INSERT) {
-                store_new_row(rows + sel, r, V, sel_action, fl);
+                store_hot(hp, fresh_hot(r, V, sel_action, fl));
+                if (parent_is_root) store_hot(rows + sel, fresh_hot(r, V, sel_action, fl));  // defined but unused mirror
             } else {
-                rows[sel].r = r;
-                rows[sel].V = V;
-                rows[sel].nn_flags = fl;
+                CHot* h = reinterpret_cast<CHot*>(hp);
+                h->r = r; h->V = V; h->nn_flags = fl;
             }
-            p.cstate[(size_t)t * p.R + sel] = make_double2(nth, nthdot);
+            store_sec1_new(rows + sel, nth, nthdot);
             p.X[t] = env::pendulum_obs(nth, nthdot);
-            p.leaf[t] = sel | LEAF_EVAL | (term ? LEAF_TERMINAL : 0);
+            c.leaf = sel | LEAF_EVAL | (term ? LEAF_TERMINAL : 0) | (parent_is_root ? (LEAF_ROOTCHILD | (jsel << LEAF_J_SHIFT)) : 0);
             // first backup step R = r + gamma*V: with tapes V is known here, otherwise the evaluation kernel adds it
-            p.leafR[t] = p.use_tape ? r + (double)__fmul_rn(p.gamma_f32, V) : r;
+            c.leafR = p.use_tape ? r + (double)__fmul_rn(p.gamma_f32, V) : r;
         } else if (kind == KIND_TERMINAL) {
-            p.leaf[t] = cur;
-            p.leafR[t] = leaf_r + (double)__fmul_rn(p.gamma_f32, 0.0f);
+            c.leaf = cur;
+            c.leafR = leaf_r + (double)__fmul_rn(p.gamma_f32, 0.0f);
             p.ctr[(size_t)2 * p.B + t] += 1;
         } else {
-            p.leaf[t] = 0;
+            c.leaf = 0;
             depth = 0;
         }
-        p.n_rows[t] = n_rows;
-        p.draws[t] = draws;
-        p.pw[t] = pwc;
-        p.depth[t] = depth;
+        c.n_rows = (uint8_t)n_rows;
+        c.draws = draws;
+        c.pw = (uint16_t)pwc;
+        c.depth = (uint8_t)depth;
         p.ctr[t] += levels;
         p.ctr[(size_t)p.B + t] += scanned;
+        memcpy(c.root_kids, rootk, 16);
     }
+    memcpy(c.path, pathw, 16);
+    store_ctl(p.ctl + t, c);
 }
 
 // numpy pairwise summation for n <= 128 (np.sum in get_on_policy_value_target, mcts.py:111)
@@ -284,22 +357,23 @@ __device__ __forceinline__ double np_sum(const double* a, int n) {
     return res;
 }
 
-// MCTS.return_results (mcts.py:269-307): root children in insertion order, one thread per tree
+// MCTS.return_results (mcts.py:269-307): root children in insertion order = the root edge table, one thread per tree
 __global__ void k_results_continuous(const TreeParams p, int cmax, float* actions, int32_t* counts, double* Q, double* Vt,
                                      int32_t* nchild) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.B) return;
-    const CRow* rows = p.crows + (size_t)t * p.R;
-    const float Vroot = rows[0].V;
-    const int nk = min((int)rows[0].nkids, cmax);
-    double q[CROW_MAX_KIDS + 1];
-    int32_t cn[CROW_MAX_KIDS + 1];
+    const CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
+    const CCtl c = load_ctl(p.ctl + t);
+    const float Vroot = c.root_V;
+    const int nk = min((int)c.root_nk, cmax);
+    double q[CROOT_MAX_KIDS];
+    int32_t cn[CROOT_MAX_KIDS];
     for (int j = 0; j < nk; ++j) {
-        const CHot c = load_hot(rows + rows[0].kids[j]);
-        q[j] = c.n_e > 0 ? c.W / (double)c.n_e : (double)Vroot;
-        cn[j] = c.n_e;
-        actions[(size_t)t * cmax + j] = c.action;
-        counts[(size_t)t * cmax + j] = c.n_e;
+        const CHot h = load_hot(et + j);
+        q[j] = h.n_e > 0 ? h.W / (double)h.n_e : (double)Vroot;
+        cn[j] = h.n_e;
+        actions[(size_t)t * cmax + j] = h.action;
+        counts[(size_t)t * cmax + j] = h.n_e;
         Q[(size_t)t * cmax + j] = q[j];
     }
     for (int j = nk; j < cmax; ++j) {

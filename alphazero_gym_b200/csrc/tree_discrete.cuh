@@ -49,8 +49,6 @@ __global__ void k_init_discrete(const TreeParams p) {
     p.leaf[t] = 0 | LEAF_EVAL;
     p.n_rows[t] = 1;
     p.draws[t] = 0;
-    p.pw[t] = 0;
-    p.depth[t] = 0;
     for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
 }
 
