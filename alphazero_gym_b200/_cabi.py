@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libazg.so")
+LIB_PATH = os.environ.get("AZG_LIB_PATH") or os.path.join(HERE, "lib", "libazg.so")  # override: kernel experiments only
 
 AZG_OK, AZG_EINVAL, AZG_ECUDA, AZG_ETERMINAL, AZG_ENAN, AZG_ECAPACITY = 0, -1, -2, -3, -4, -5
 DISCRETE, CONTINUOUS = 0, 1

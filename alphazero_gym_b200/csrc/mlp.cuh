@@ -154,15 +154,17 @@ __device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const
     constexpr int TU = MLP_UNIT;
     const int lane = gt & 31, wc = gt >> 5;  // warp column block (32 cols)
     const int row0 = (lane & 7) * 4, col0 = wc * 32 + (lane >> 3) * 8;
-#ifndef MLP_SCALAR_FMA
-    float2 acc[4][4];  // [row][column pair]
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float2 bc = *reinterpret_cast<const float2*>(b + col0 + 2 * c);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[r][c] = bc;
-    }
-#else
+#ifndef MLP_UNROLL
+#define MLP_UNROLL 16
+#endif
+#define MLP_STR2(x) #x
+#define MLP_STR(x) MLP_STR2(x)
+    const float* ap = actg + row0;
+    const float* wp = Wt + col0;
+    float4 a = *reinterpret_cast<const float4*>(ap);
+    float4 w0 = *reinterpret_cast<const float4*>(wp);
+    float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+    // accumulators paired along columns: acc[r][c] = (column 2c, column 2c+1) of row r; the activation is the scalar operand
     float2 acc[4][4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -170,13 +172,7 @@ __device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const
 #pragma unroll
         for (int r = 0; r < 4; ++r) acc[r][c] = bc;
     }
-#endif
-    const float* ap = actg + row0;
-    const float* wp = Wt + col0;
-    float4 a = *reinterpret_cast<const float4*>(ap);
-    float4 w0 = *reinterpret_cast<const float4*>(wp);
-    float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
-#pragma unroll 8
+    _Pragma(MLP_STR(unroll MLP_UNROLL))
     for (int k = 0; k < H; ++k) {
         const int kn = k + 1 < H ? k + 1 : k;  // the last iteration re-reads row k (discarded)
         const float4 na = *reinterpret_cast<const float4*>(ap + kn * TU);
@@ -186,17 +182,9 @@ __device__ __forceinline__ void hidden_layer(const float* __restrict__ Wt, const
         const float2 wpair[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-#ifndef MLP_SCALAR_FMA
             const float2 av = make_float2(ar[r], ar[r]);
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[r][c] = __ffma2_rn(av, wpair[c], acc[r][c]);
-#else
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                acc[r][c].x = __fmaf_rn(ar[r], wpair[c].x, acc[r][c].x);
-                acc[r][c].y = __fmaf_rn(ar[r], wpair[c].y, acc[r][c].y);
-            }
-#endif
         }
         a = na; w0 = nw0; w1 = nw1;
     }
