@@ -16,6 +16,7 @@ DISCRETE, CONTINUOUS = 0, 1
 ACT_RELU, ACT_ELU = 0, 1
 VT = {"off_policy": 0, "on_policy": 1, "greedy": 2}
 FLAG_NO_GRAPH = 1
+FLAG_EVAL_Q8 = 2
 
 EXPORTS = [
     "azg_create", "azg_destroy", "azg_last_error", "azg_version", "azg_num_weights", "azg_set_weights",

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "env.cuh"
 #include "mlp.cuh"
+#include "qmlp.cuh"
 #include "tree_continuous.cuh"
 #include "tree_discrete.cuh"
 
@@ -56,6 +57,12 @@ struct azg_engine {
     int32_t* root_n_init = nullptr;
     int32_t* err = nullptr;
     float* wpack = nullptr;
+    // AZG_FLAG_EVAL_Q8: int8 digit planes + f32 side table of the tensor-core evaluation kernel (qmlp.cuh)
+    int8_t* qdigits = nullptr;
+    float* qfl = nullptr;
+    int qfl_count = 0;
+    size_t qmlp_smem = 0;
+    bool q8 = false;
     // results staging (device) + pinned host staging for the *_host entry point
     float* r_actions = nullptr;
     int32_t* r_counts = nullptr;
@@ -96,7 +103,7 @@ extern "C" void azg_destroy(azg_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     void* ptrs[] = {e->drows, e->dstate, e->crows, e->et, e->ctl, e->chead, e->pw_table, e->n_rows, e->draws,
-                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->r_actions,
+                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->qdigits, e->qfl, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -149,6 +156,15 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
         delete e;
         return fail(AZG_EINVAL, "network does not fit in shared memory");
     }
+    e->q8 = (c.flags & AZG_FLAG_EVAL_Q8) != 0;
+    if (e->q8) {
+        e->qfl_count = (c.state_dim * H + H + (c.n_hidden - 1) * 2 * H + H * e->PO_PAD + e->PO_PAD + 3) / 4 * 4;
+        e->qmlp_smem = qmlp_smem_bytes(c.n_hidden - 1, e->qfl_count, e->PO_PAD);
+        if (H != 128 || c.n_hidden < 2 || c.n_hidden > 3 || e->qmlp_smem > (size_t)prop.sharedMemPerBlockOptin || prop.major != 10) {
+            delete e;
+            return fail(AZG_EINVAL, "AZG_FLAG_EVAL_Q8 needs hidden = 128, n_hidden in {2, 3} and an sm_100 device (tcgen05)");
+        }
+    }
     const size_t B = c.max_trees, R = e->R;
     std::vector<int32_t> pwt;
     if (c.variant == AZG_CONTINUOUS) {
@@ -194,6 +210,10 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(root_n_init, B);
     ALLOC(err, 1);
     ALLOC(wpack, (size_t)e->wcount);
+    if (e->q8) {
+        ALLOC(qdigits, (size_t)(c.n_hidden - 1) * 3 * QMLP_PLANE);
+        ALLOC(qfl, (size_t)e->qfl_count);
+    }
     ALLOC(r_actions, B * e->cmax); ALLOC(r_counts, B * e->cmax); ALLOC(r_Q, B * e->cmax); ALLOC(r_Vt, B); ALLOC(r_nchild, B);
 #undef ALLOC
     CK(cudaMemset(e->err, 0, sizeof(int32_t)));
@@ -248,6 +268,61 @@ static void pack_weights(const azg_engine* e, const float* w, std::vector<float>
     for (int q = 0; q < P; ++q) d[1 + q] = bd[q];
 }
 
+// AZG_FLAG_EVAL_Q8 packing (contract: oracle/azg_oracle.h "AZO_EVAL_Q8"; consumer: qmlp.cuh).  Hidden layer l >= 1, output j:
+// e = clamp(biased_exponent(max_k |W[j][k]| * 1.004f), 32, 200); Wq = rni(W * 2^(149-e)); balanced base-256 digits = bytes of
+// (Wq + 0x8080) ^ 0x8080; planes (hi, mid, lo) in the UMMA K-major canonical layout [k/16][j][16]; cw[j] = 2^(e-133).
+static void pack_weights_q8(const azg_engine* e, const float* w, std::vector<int8_t>& digits, std::vector<float>& fl) {
+    const int H = e->cfg.hidden, S = e->cfg.state_dim, L = e->cfg.n_hidden, P = e->P, PO = e->PO_PAD;
+    digits.assign((size_t)(L - 1) * 3 * QMLP_PLANE, 0);
+    fl.assign(e->qfl_count, 0.0f);
+    float* d = fl.data();
+    for (int j = 0; j < H; ++j)
+        for (int k = 0; k < S; ++k) d[(size_t)k * H + j] = w[(size_t)j * S + k];
+    d += (size_t)S * H;
+    w += (size_t)S * H;
+    memcpy(d, w, H * sizeof(float));
+    d += H;
+    w += H;
+    auto bits = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto from_bits = [](uint32_t u) { float f; memcpy(&f, &u, 4); return f; };
+    for (int l = 1; l < L; ++l) {
+        int8_t* pl = digits.data() + (size_t)(l - 1) * 3 * QMLP_PLANE;
+        for (int j = 0; j < H; ++j) {
+            float wmax = 0.0f;
+            for (int k = 0; k < H; ++k) wmax = fmaxf(wmax, fabsf(w[(size_t)j * H + k]));
+            volatile float scaled = wmax * 1.004f;
+            int ex = (int)((bits(scaled) >> 23) & 0xFF);
+            ex = ex < 32 ? 32 : (ex > 200 ? 200 : ex);
+            const float sc = from_bits((uint32_t)(276 - ex) << 23);
+            d[2 * j] = from_bits((uint32_t)(ex - 6) << 23);
+            d[2 * j + 1] = w[(size_t)H * H + j];
+            for (int k = 0; k < H; ++k) {
+                volatile float tq = w[(size_t)j * H + k] * sc;
+                const float tv = tq;
+                int32_t q = tv != tv ? 0 : (tv >= 2147483648.0f ? INT32_MAX : (tv <= -2147483648.0f ? INT32_MIN : (int32_t)nearbyintf(tv)));
+                const uint32_t t = ((uint32_t)q + 0x8080u) ^ 0x8080u;
+                const size_t o = (size_t)(k / 16) * 2048 + (size_t)j * 16 + (k % 16);
+                pl[o] = (int8_t)((t >> 16) & 0xFF);
+                pl[QMLP_PLANE + o] = (int8_t)((t >> 8) & 0xFF);
+                pl[2 * QMLP_PLANE + o] = (int8_t)(t & 0xFF);
+            }
+        }
+        d += 2 * H;
+        w += (size_t)H * H + H;
+    }
+    const float* wv = w;
+    const float* bv = w + H;
+    const float* wd = w + H + 1;
+    const float* bd = wd + (size_t)P * H;
+    for (int k = 0; k < H; ++k) {
+        d[(size_t)k * PO] = wv[k];
+        for (int q = 0; q < P; ++q) d[(size_t)k * PO + 1 + q] = wd[(size_t)q * H + k];
+    }
+    d += (size_t)H * PO;
+    d[0] = bv[0];
+    for (int q = 0; q < P; ++q) d[1 + q] = bd[q];
+}
+
 extern "C" int azg_set_weights(azg_engine* e, const float* flat, int64_t n, void* stream) {
     if (!e || !flat) return fail(AZG_EINVAL, "null argument");
     if (n != e->n_weights) return fail(AZG_EINVAL, "weight count " + std::to_string(n) + " != expected " + std::to_string(e->n_weights));
@@ -266,6 +341,13 @@ extern "C" int azg_set_weights(azg_engine* e, const float* flat, int64_t n, void
     std::vector<float> packed;
     pack_weights(e, host.data(), packed);
     CK(cudaMemcpyAsync(e->wpack, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    std::vector<int8_t> qd;
+    std::vector<float> qf;
+    if (e->q8) {
+        pack_weights_q8(e, host.data(), qd, qf);
+        CK(cudaMemcpyAsync(e->qdigits, qd.data(), qd.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->qfl, qf.data(), qf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
     CK(cudaStreamSynchronize(st));
     e->weights_set = true;
     return AZG_OK;
@@ -312,6 +394,7 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     m.leaf = e->leaf; m.drows = e->drows; m.crows = e->crows; m.chead = e->chead; m.evals = e->ctr + (size_t)3 * n;
     m.ctl = e->ctl; m.et = e->et; m.gamma_f32 = (float)c.gamma;
     m.head_dim = azg_head_dim(e);
+    m.qdigits = e->qdigits; m.qfl = e->qfl; m.qfl_count = e->qfl_count;
     return m;
 }
 
@@ -324,8 +407,25 @@ static cudaError_t launch_mlp_t(const azg_engine* e, const MlpParams& m, cudaStr
     return cudaGetLastError();
 }
 
+template <int S, int ACT, int NL>
+static cudaError_t launch_qmlp_t(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr) {
+    if (set_attr) return cudaFuncSetAttribute(k_qmlp<S, ACT, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
+    const int grid = std::max(1, std::min((m.n + 127) / 128, e->sm_count));
+    k_qmlp<S, ACT, NL><<<grid, QMLP_THREADS, e->qmlp_smem, st>>>(m);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr) {
     const int H = e->cfg.hidden, S = e->cfg.state_dim, A = e->cfg.activation;
+    if (e->q8) {
+        const int NL = e->cfg.n_hidden - 1;
+#define QMLP_CASE(s, a, nl) \
+    if (S == s && A == a && NL == nl) return launch_qmlp_t<s, a, nl>(e, m, st, set_attr);
+        QMLP_CASE(4, 0, 1) QMLP_CASE(4, 1, 1) QMLP_CASE(3, 0, 1) QMLP_CASE(3, 1, 1)
+        QMLP_CASE(4, 0, 2) QMLP_CASE(4, 1, 2) QMLP_CASE(3, 0, 2) QMLP_CASE(3, 1, 2)
+#undef QMLP_CASE
+        return cudaErrorInvalidValue;
+    }
 #define MLP_CASE(h, s, a) \
     if (H == h && S == s && A == a) return launch_mlp_t<h, s, a>(e, m, st, set_attr);
     MLP_CASE(128, 4, 0) MLP_CASE(128, 4, 1) MLP_CASE(128, 3, 0) MLP_CASE(128, 3, 1)

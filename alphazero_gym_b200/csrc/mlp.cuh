@@ -46,6 +46,10 @@ struct MlpParams {
     float* outV;
     float* outHead;
     int32_t head_dim;
+    // AZG_FLAG_EVAL_Q8 (qmlp.cuh): int8 digit planes [L-1][3][H/16][H][16] and the f32 side table (engine.cu pack_weights_q8)
+    const int8_t* qdigits;
+    const float* qfl;
+    int32_t qfl_count;  // floats in qfl (multiple of 4)
 };
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP / SYNCS) --------------
@@ -129,6 +133,48 @@ __device__ __forceinline__ void softmax_seq(const float* l, int n, float* p) {
         s = __fadd_rn(s, p[i]);
     }
     for (int i = 0; i < n; ++i) p[i] = __fdiv_rn(p[i], s);
+}
+
+// post-processing + write-back of one evaluated row: V and the raw policy-head outputs -> softmax priors / GMM parameters ->
+// the tree tables (mode 0) or dense outputs (mode 1).  Shared by k_mlp and k_qmlp.
+__device__ __forceinline__ void mlp_finish_row(const MlpParams& p, int gr, int leafw, double lr, float V, const float* raw) {
+    float post[3 * AZG_MAX_K];
+    int npost;
+    if (p.variant == 0) {
+        softmax_seq(raw, p.A, post);
+        npost = p.A;
+    } else {
+        const int K = p.K;
+        for (int k = 0; k < K; ++k) {
+            post[k] = raw[k];
+            float ls = raw[K + k];
+            ls = ls < p.ls_min ? p.ls_min : ls;
+            ls = ls > p.ls_max ? p.ls_max : ls;
+            post[K + k] = det::expf_(ls);
+        }
+        if (K > 1) softmax_seq(raw + 2 * K, K, post + 2 * K);
+        else post[2] = 1.0f;
+        npost = 3 * K;
+    }
+    if (p.mode == 1) {
+        p.outV[gr] = V;
+        for (int i = 0; i < npost; ++i) p.outHead[(size_t)gr * p.head_dim + i] = post[i];
+    } else {
+        const size_t ri = (size_t)gr * p.R + (leafw & LEAF_ROW_MASK);
+        if (leafw & LEAF_TERMINAL) V = 0.0f;  // mcts.py:406-410, :619-623
+        if (p.variant == 0) {
+            DRow* d = p.drows + ri;
+            d->V = V;
+            *reinterpret_cast<float2*>(d->prior) = make_float2(post[0], post[1]);
+        } else {
+            if (leafw & LEAF_ROOTCHILD) p.et[(size_t)gr * CROOT_MAX_KIDS + ((leafw >> LEAF_J_SHIFT) & 0xFF)].V = V;
+            else p.crows[ri].V = V;
+            p.ctl[gr].leafR = lr + (double)__fmul_rn(p.gamma_f32, V);
+            float* h = p.chead + ri * p.HS;
+            for (int i = 0; i < npost; ++i) h[i] = post[i];
+        }
+        p.evals[gr] += 1;
+    }
 }
 
 // Thread mapping.  The CTA (512 threads for H = 128) is split into NGRP = 4 independent groups of H/32
@@ -282,45 +328,9 @@ __device__ __forceinline__ void mlp_unit(const MlpParams& p, const float* w, flo
     // ahead into the next unit's layer 0 (they only touch actg, and outg is not rewritten before two more
     // group barriers that warp 0 takes part in)
     if (q == 0 && need) {
-        float V = outg[row];
-        float raw[3 * AZG_MAX_K], post[3 * AZG_MAX_K];
+        float raw[3 * AZG_MAX_K];
         for (int i = 0; i < p.P; ++i) raw[i] = outg[(1 + i) * TU + row];
-        int npost;
-        if (p.variant == 0) {
-            softmax_seq(raw, p.A, post);
-            npost = p.A;
-        } else {
-            const int K = p.K;
-            for (int k = 0; k < K; ++k) {
-                post[k] = raw[k];
-                float ls = raw[K + k];
-                ls = ls < p.ls_min ? p.ls_min : ls;
-                ls = ls > p.ls_max ? p.ls_max : ls;
-                post[K + k] = det::expf_(ls);
-            }
-            if (K > 1) softmax_seq(raw + 2 * K, K, post + 2 * K);
-            else post[2] = 1.0f;
-            npost = 3 * K;
-        }
-        if (p.mode == 1) {
-            p.outV[gr] = V;
-            for (int i = 0; i < npost; ++i) p.outHead[(size_t)gr * p.head_dim + i] = post[i];
-        } else {
-            const size_t ri = (size_t)gr * p.R + (leafw & LEAF_ROW_MASK);
-            if (leafw & LEAF_TERMINAL) V = 0.0f;  // mcts.py:406-410, :619-623
-            if (p.variant == 0) {
-                DRow* d = p.drows + ri;
-                d->V = V;
-                *reinterpret_cast<float2*>(d->prior) = make_float2(post[0], post[1]);
-            } else {
-                if (leafw & LEAF_ROOTCHILD) p.et[(size_t)gr * CROOT_MAX_KIDS + ((leafw >> LEAF_J_SHIFT) & 0xFF)].V = V;
-                else p.crows[ri].V = V;
-                p.ctl[gr].leafR = lr + (double)__fmul_rn(p.gamma_f32, V);
-                float* h = p.chead + ri * p.HS;
-                for (int i = 0; i < npost; ++i) h[i] = post[i];
-            }
-            p.evals[gr] += 1;
-        }
+        mlp_finish_row(p, gr, leafw, lr, outg[row], raw);
     }
 }
 

@@ -62,6 +62,10 @@ typedef struct azg_config {
 } azg_config;
 
 #define AZG_FLAG_NO_GRAPH 1u /* launch kernels directly instead of replaying a captured CUDA graph */
+#define AZG_FLAG_EVAL_Q8 2u  /* evaluate the hidden x hidden layers on the tensor cores (tcgen05.mma kind::i8) as exact
+                                int8-sliced fixed-point products instead of FP32 FMA; needs hidden = 128, n_hidden in {2,3}.
+                                Deterministic and bit-reproducible by the CPU oracle (AZO_EVAL_Q8); V error vs an f64
+                                evaluation is ~2x that of the FP32 path, well inside the 1e-5 parity tolerance. */
 
 typedef struct azg_engine azg_engine;
 

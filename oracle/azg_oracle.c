@@ -244,11 +244,57 @@ typedef struct {
     const float* b[AZO_MAX_LAYERS];
     const float *wv, *bv, *wd, *bd;
     float* owned;
+    /* AZO_EVAL_Q8: digit planes [3][H][H] (row j, column k) and per-output scale of every hidden layer l >= 1 */
+    int8_t* qd[AZO_MAX_LAYERS];
+    float* qcw[AZO_MAX_LAYERS];
 } net_t;
+
+static inline int biased_exp_clamped(float f) {
+    int e = (int)((f32_bits(f) >> 23) & 0xFF);
+    return e < 32 ? 32 : (e > 200 ? 200 : e);
+}
+/* cvt.rni.s32.f32: round to nearest even, saturating, NaN -> 0 */
+static inline int32_t rni_sat(float t) {
+    if (t != t) return 0;
+    if (t >= 2147483648.0f) return INT32_MAX;
+    if (t <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)rintf(t);
+}
+
+/* balanced signed base-256 digits of q (|q| <= 8355711): bytes of (q + 0x8080) with the two low bytes' top bit flipped */
+static inline void q8_digits(int32_t q, int8_t* hi, int8_t* mid, int8_t* lo) {
+    const uint32_t t = ((uint32_t)q + 0x8080u) ^ 0x8080u;
+    *lo = (int8_t)(t & 0xFF);
+    *mid = (int8_t)((t >> 8) & 0xFF);
+    *hi = (int8_t)((t >> 16) & 0xFF);
+}
+/* biased exponent e such that |v| * 2^(149-e) <= 8355711 for every |v| <= vmax (1.004 keeps the top digit in int8) */
+static inline int q8_exponent(float vmax) { return biased_exp_clamped(vmax * 1.004f); }
+
+static void net_quantize(net_t* n, const float* w_state_dict) {
+    const int H = n->H;
+    const float* w = w_state_dict + (size_t)n->S * H + H;
+    for (int l = 1; l < n->L; ++l) {
+        n->qd[l] = (int8_t*)malloc((size_t)3 * H * H);
+        n->qcw[l] = (float*)malloc((size_t)H * sizeof(float));
+        for (int j = 0; j < H; ++j) {
+            float wmax = 0.0f;
+            for (int k = 0; k < H; ++k) wmax = fmaxf(wmax, fabsf(w[(size_t)j * H + k]));
+            const int e = q8_exponent(wmax);
+            const float sc = f32_from_bits((uint32_t)(276 - e) << 23); /* 2^(149-e) */
+            n->qcw[l][j] = f32_from_bits((uint32_t)(e - 6) << 23);      /* 2^(e-133) = 2^16 / sc */
+            for (int k = 0; k < H; ++k)
+                q8_digits(rni_sat(w[(size_t)j * H + k] * sc), &n->qd[l][(size_t)j * H + k], &n->qd[l][(size_t)H * H + (size_t)j * H + k],
+                          &n->qd[l][(size_t)2 * H * H + (size_t)j * H + k]);
+        }
+        w += (size_t)H * H + H;
+    }
+}
 
 static int net_init(net_t* n, const azo_config* c, const float* w, int64_t nw) {
     if (c->n_hidden < 1 || c->n_hidden > AZO_MAX_LAYERS || c->hidden < 1 || nw != azo_num_weights(c)) return -2;
     n->S = c->state_dim; n->H = c->hidden; n->L = c->n_hidden; n->P = azo_head_dim(c);
+    const float* w0 = w;
     size_t tot = (size_t)n->S * n->H + (size_t)(n->L - 1) * n->H * n->H;
     n->owned = (float*)malloc(tot * sizeof(float));
     float* dst = n->owned;
@@ -266,10 +312,18 @@ static int net_init(net_t* n, const azo_config* c, const float* w, int64_t nw) {
     n->bv = w; w += 1;
     n->wd = w; w += (size_t)n->P * n->H;
     n->bd = w;
+    for (int l = 0; l < AZO_MAX_LAYERS; ++l) { n->qd[l] = NULL; n->qcw[l] = NULL; }
+    if (c->eval_mode == AZO_EVAL_Q8) {
+        if (n->H % 32 != 0) return -2;
+        net_quantize(n, w0);
+    }
     return 0;
 }
 
-static void net_free(net_t* n) { free(n->owned); n->owned = NULL; }
+static void net_free(net_t* n) {
+    free(n->owned); n->owned = NULL;
+    for (int l = 0; l < AZO_MAX_LAYERS; ++l) { free(n->qd[l]); free(n->qcw[l]); n->qd[l] = NULL; n->qcw[l] = NULL; }
+}
 
 static inline float act_fn(const azo_config* c, float v) {
     if (c->activation == AZO_ACT_RELU) return v > 0.0f ? v : 0.0f;
@@ -278,23 +332,76 @@ static inline float act_fn(const azo_config* c, float v) {
     return c->math_mode == AZO_MATH_DET ? azo_det_expm1f(v) : expm1f(v);
 }
 
+/* one hidden layer of the AZO_EVAL_Q8 contract (azg_oracle.h) */
+static void q8_layer(const net_t* n, const azo_config* c, int l, const float* in, float* out) {
+    const int H = n->H;
+    int8_t xh[1024], xm[1024], xl[1024];
+    float m = 0.0f;
+    for (int k = 0; k < H; ++k) m = fmaxf(m, fabsf(in[k]));
+    const int e = q8_exponent(m);
+    const float sx = f32_from_bits((uint32_t)(276 - e) << 23); /* 2^(149-e) */
+    const float cx = f32_from_bits((uint32_t)(e - 22) << 23);  /* 2^(e-149) */
+    for (int k = 0; k < H; ++k) q8_digits(rni_sat(in[k] * sx), &xh[k], &xm[k], &xl[k]);
+    const int8_t* dh = n->qd[l];
+    const int8_t* dm = dh + (size_t)H * H;
+    const int8_t* dl = dm + (size_t)H * H;
+    for (int j = 0; j < H; ++j) {
+        const int8_t* wh = dh + (size_t)j * H;
+        const int8_t* wm = dm + (size_t)j * H;
+        const int8_t* wl = dl + (size_t)j * H;
+        int32_t PA = 0, PB = 0, PC = 0;
+        for (int k = 0; k < H; ++k) {
+            const int32_t a2 = xh[k], a1 = xm[k], a0 = xl[k];
+            PA += a2 * wh[k];
+            PB += a2 * wm[k] + a1 * wh[k];
+            PC += a2 * wl[k] + a1 * wm[k] + a0 * wh[k];
+        }
+        float u = fmaf((float)PA, 256.0f, (float)PB);
+        u = fmaf(u, 256.0f, (float)PC);
+        out[j] = act_fn(c, fmaf(u, cx * n->qcw[l][j], n->b[l][j]));
+    }
+}
+
+static inline float q8_head(const float* w, const float* in, int H, float bias) {
+    float part[32];
+    const int nq = H / 32;
+    for (int q = 0; q < nq; ++q) {
+        float s = 0.0f;
+        for (int k = 32 * q; k < 32 * q + 32; ++k) s = fmaf(in[k], w[k], s);
+        part[q] = s;
+    }
+    for (int span = 1; span < nq; span *= 2)
+        for (int q = 0; q + span < nq; q += 2 * span) part[q] = part[q] + part[q + span];
+    return part[0] + bias;
+}
+
 static void net_forward(const net_t* n, const azo_config* c, const float* x, float* V, float* head) {
     float h0[1024], h1[1024];
     float* in = h0;
     float* out = h1;
     const int H = n->H;
+    const int q8 = c->eval_mode == AZO_EVAL_Q8;
     for (int k = 0; k < n->S; ++k) in[k] = x[k];
     for (int l = 0; l < n->L; ++l) {
-        int K = l == 0 ? n->S : H;
-        const float* wt = n->wt[l];
-        for (int j = 0; j < H; ++j) out[j] = n->b[l][j];
-        for (int k = 0; k < K; ++k) {
-            const float xk = in[k];
-            const float* wr = wt + (size_t)k * H;
-            for (int j = 0; j < H; ++j) out[j] = __builtin_fmaf(wr[j], xk, out[j]);
+        if (q8 && l > 0) {
+            q8_layer(n, c, l, in, out);
+        } else {
+            int K = l == 0 ? n->S : H;
+            const float* wt = n->wt[l];
+            for (int j = 0; j < H; ++j) out[j] = n->b[l][j];
+            for (int k = 0; k < K; ++k) {
+                const float xk = in[k];
+                const float* wr = wt + (size_t)k * H;
+                for (int j = 0; j < H; ++j) out[j] = __builtin_fmaf(wr[j], xk, out[j]);
+            }
+            for (int j = 0; j < H; ++j) out[j] = act_fn(c, out[j]);
         }
-        for (int j = 0; j < H; ++j) out[j] = act_fn(c, out[j]);
         float* t = in; in = out; out = t;
+    }
+    if (q8) {
+        *V = q8_head(n->wv, in, H, n->bv[0]);
+        for (int p = 0; p < n->P; ++p) head[p] = q8_head(n->wd + (size_t)p * H, in, H, n->bd[p]);
+        return;
     }
     float acc = n->bv[0];
     for (int k = 0; k < H; ++k) acc = fmaf(n->wv[k], in[k], acc);

@@ -49,6 +49,9 @@ extern "C" {
 #define AZO_MATH_LIBM 0 /* glibc sin/cos/expf/... : what the python reference calls */
 #define AZO_MATH_DET 1  /* op-for-op deterministic functions shared (as a spec) with the CUDA engine */
 
+#define AZO_EVAL_FP32 0 /* every layer in FP32 FMA, k ascending (csrc/mlp.cuh) */
+#define AZO_EVAL_Q8 1   /* hidden x hidden layers as exact int8-sliced fixed-point products (csrc/qmlp.cuh; contract below) */
+
 #define AZO_VT_OFF_POLICY 0
 #define AZO_VT_ON_POLICY 1
 #define AZO_VT_GREEDY 2
@@ -73,7 +76,24 @@ typedef struct {
     double c_uct, gamma, epsilon, c_pw, kappa;
     float action_bound, log_std_min, log_std_max;
     uint64_t seed;         /* Philox key */
+    int32_t eval_mode;     /* AZO_EVAL_* */
+    int32_t reserved_;
 } azo_config;
+
+/* AZO_EVAL_Q8 contract (the arithmetic the tcgen05 kind::i8 kernel performs; every step is exact integer
+ * arithmetic or one correctly rounded IEEE f32 operation, so CPU and GPU agree bit for bit):
+ *   layer 0 (state_dim -> H): FP32 FMA as in AZO_EVAL_FP32.
+ *   scaling: for a vector with largest magnitude vmax, e = clamp(biased_exponent(f32(vmax * 1.004f)), 32, 200) and
+ *     q = rni_sat(v * 2^(149-e)), so |q| <= 8355711 and the balanced signed base-256 digits q = hi*2^16 + mid*2^8 + lo
+ *     (bytes of (q + 0x8080) ^ 0x8080) all fit int8.
+ *   weights of a hidden layer: one scale per output j (vmax over k);  cw[j] = 2^(e-133).
+ *   activations: one scale per row (vmax over the H inputs of the layer);  cx = 2^(e-149).
+ *   products (int32, exact):  PA = sum xh*wh;  PB = sum xh*wm + xm*wh;  PC = sum xh*wl + xm*wm + xl*wh
+ *     (order-5/6 digit products dropped: relative weight <= 2^-24 of the leading product; measured error of V
+ *     against an f64 evaluation is 2x that of the FP32 path, tests/test_q8_eval.py).
+ *   y[j] = fma(fma(fma((f32)PA, 256, (f32)PB), 256, (f32)PC), cx * cw[j], bias[j]);  a'[j] = act(y[j]).
+ *   heads: partial[q] = fma chain over k in [32q, 32q+32) from 0;  out = ((p0 + p1) + (p2 + p3)) + bias
+ *     (for H = 128; in general H/32 partials summed pairwise left to right). */
 
 /* Row counts: a search of N rollouts creates at most N+1 nodes (root + one per rollout);
  * the continuous tree can hold one extra unexpanded root edge (c_pw > 1), hence N+2 rows. */

@@ -11,7 +11,8 @@ def engine_config(cfg: azo.Config, max_trees: int, **kw) -> EngineConfig:
              num_components=cfg.num_components, state_dim=cfg.state_dim, hidden=cfg.hidden, n_hidden=cfg.n_hidden,
              activation=cfg.activation, V_target_policy=cfg.V_target_policy, puct_f32=cfg.puct_f32, c_uct=cfg.c_uct,
              gamma=cfg.gamma, epsilon=cfg.epsilon, c_pw=cfg.c_pw, kappa=cfg.kappa, action_bound=cfg.action_bound,
-             log_std_min=cfg.log_std_min, log_std_max=cfg.log_std_max, seed=cfg.seed)
+             log_std_min=cfg.log_std_min, log_std_max=cfg.log_std_max, seed=cfg.seed,
+             eval_q8=cfg.eval_mode == azo.EVAL_Q8)
     d.update(kw)
     return EngineConfig(**d)
 
