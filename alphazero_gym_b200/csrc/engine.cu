@@ -19,6 +19,7 @@
 #include "env.cuh"
 #include "mlp.cuh"
 #include "qmlp.cuh"
+#include "qmlp2.cuh"
 #include "tree_continuous.cuh"
 #include "tree_discrete.cuh"
 
@@ -159,10 +160,11 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     e->q8 = (c.flags & AZG_FLAG_EVAL_Q8) != 0;
     if (e->q8) {
         e->qfl_count = (c.state_dim * H + H + (c.n_hidden - 1) * 2 * H + H * e->PO_PAD + e->PO_PAD + 3) / 4 * 4;
-        e->qmlp_smem = qmlp_smem_bytes(c.n_hidden - 1, e->qfl_count, e->PO_PAD);
-        if (H != 128 || c.n_hidden < 2 || c.n_hidden > 3 || e->qmlp_smem > (size_t)prop.sharedMemPerBlockOptin || prop.major != 10) {
+        e->qmlp_smem = qmlp2_smem_bytes(c.n_hidden - 1, e->qfl_count);
+        if (H != 128 || c.n_hidden < 2 || c.n_hidden > 3 || e->PO_PAD > Q2_MAX_PO || e->qmlp_smem > (size_t)prop.sharedMemPerBlockOptin ||
+            prop.major != 10) {
             delete e;
-            return fail(AZG_EINVAL, "AZG_FLAG_EVAL_Q8 needs hidden = 128, n_hidden in {2, 3} and an sm_100 device (tcgen05)");
+            return fail(AZG_EINVAL, "AZG_FLAG_EVAL_Q8 needs hidden = 128, n_hidden in {2, 3}, at most 15 head outputs and an sm_100 device (tcgen05)");
         }
     }
     const size_t B = c.max_trees, R = e->R;
@@ -301,7 +303,7 @@ static void pack_weights_q8(const azg_engine* e, const float* w, std::vector<int
                 const float tv = tq;
                 int32_t q = tv != tv ? 0 : (tv >= 2147483648.0f ? INT32_MAX : (tv <= -2147483648.0f ? INT32_MIN : (int32_t)nearbyintf(tv)));
                 const uint32_t t = ((uint32_t)q + 0x8080u) ^ 0x8080u;
-                const size_t o = (size_t)(k / 16) * 2048 + (size_t)j * 16 + (k % 16);
+                const size_t o = (size_t)(k / 16) * 2048 + (size_t)qmlp_perm_row(j) * 16 + (k % 16);
                 pl[o] = (int8_t)((t >> 16) & 0xFF);
                 pl[QMLP_PLANE + o] = (int8_t)((t >> 8) & 0xFF);
                 pl[2 * QMLP_PLANE + o] = (int8_t)(t & 0xFF);
@@ -409,9 +411,9 @@ static cudaError_t launch_mlp_t(const azg_engine* e, const MlpParams& m, cudaStr
 
 template <int S, int ACT, int NL>
 static cudaError_t launch_qmlp_t(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr) {
-    if (set_attr) return cudaFuncSetAttribute(k_qmlp<S, ACT, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
+    if (set_attr) return cudaFuncSetAttribute(k_qmlp2<S, ACT, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
     const int grid = std::max(1, std::min((m.n + 127) / 128, e->sm_count));
-    k_qmlp<S, ACT, NL><<<grid, QMLP_THREADS, e->qmlp_smem, st>>>(m);
+    k_qmlp2<S, ACT, NL><<<grid, Q2_THREADS, e->qmlp_smem, st>>>(m);
     return cudaGetLastError();
 }
 

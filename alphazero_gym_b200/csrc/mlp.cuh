@@ -77,16 +77,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- activations (branch-free) -------------------------------------------------------------------------
+// rint(t) and 2^rint(t) without the conversion (XU) pipe, for t in [-2^22, 2^22]: adding 1.5 * 2^23 rounds t to the nearest-even
+// integer (the IEEE addition does the rounding) and leaves that integer in the low mantissa bits.  Same values as rintf / the
+// f32 -> s32 conversion, but FADD + integer ops instead of FRND + F2I, which run at a quarter of the FMA rate and bounded the
+// evaluation kernels (profiles/r1c: XU pipe 78 % busy).
+#define MLP_RINT_MAGIC 12582912.0f
+__device__ __forceinline__ float mlp_pow2_of_magic(float tm) {  // tm = t + MAGIC  ->  2^rint(t)
+    return __uint_as_float((__float_as_uint(tm) << 23) + 0x3F800000u);
+}
+
 template <int ACT>
 __device__ __forceinline__ float mlp_act(float v) {
     if (ACT == 0) return v > 0.0f ? v : 0.0f;  // ReLU (DiscretePolicy.yaml:8)
     // ELU alpha=1 (ContinuousPolicy.yaml:9): v > 0 ? v : expm1(v), expm1 = det::expm1f_ written with selects.
-    // (n == 0 needs no special case: fma(p, 1, 0) == p; x < -17.5 is selected to -1 like the reference form.)
+    // (n == 0 needs no special case: fma(p, 1, 0) == p; x < -17.5 is selected to -1 like the reference form; for v > 0 the
+    // exponential branch is computed on garbage and discarded.)
     const float xx = fmaxf(v, -20.0f);
-    float n;
-    const float r = det::exp_reduce(xx, n);
+    const float tm = __fadd_rn(__fmul_rn(xx, 1.44269504088896341f), MLP_RINT_MAGIC);
+    const float n = __fsub_rn(tm, MLP_RINT_MAGIC);
+    float r = __fmaf_rn(n, -0.693359375f, xx);
+    r = __fmaf_rn(n, 2.12194440e-4f, r);
     const float pl = det::expm1_poly(r);
-    const float t = __uint_as_float((uint32_t)((int32_t)n + 127) << 23);
+    const float t = mlp_pow2_of_magic(tm);
     const float e = __fmaf_rn(pl, t, __fsub_rn(t, 1.0f));
     float res = v < -17.5f ? -1.0f : e;
     res = v > 0.0f ? v : res;
@@ -99,8 +111,9 @@ template <int ACT>
 __device__ __forceinline__ float2 mlp_act2(float2 v) {
     if (ACT == 0) return make_float2(v.x > 0.0f ? v.x : 0.0f, v.y > 0.0f ? v.y : 0.0f);
     const float2 xx = make_float2(fmaxf(v.x, -20.0f), fmaxf(v.y, -20.0f));
-    const float2 tn = __fmul2_rn(xx, make_float2(1.44269504088896341f, 1.44269504088896341f));
-    const float2 n = make_float2(rintf(tn.x), rintf(tn.y));
+    const float2 magic = make_float2(MLP_RINT_MAGIC, MLP_RINT_MAGIC);
+    const float2 tm = __fadd2_rn(__fmul2_rn(xx, make_float2(1.44269504088896341f, 1.44269504088896341f)), magic);
+    const float2 n = __fadd2_rn(tm, make_float2(-MLP_RINT_MAGIC, -MLP_RINT_MAGIC));
     float2 r = __ffma2_rn(n, make_float2(-0.693359375f, -0.693359375f), xx);
     r = __ffma2_rn(n, make_float2(2.12194440e-4f, 2.12194440e-4f), r);
     float2 p = make_float2(1.9875691500E-4f, 1.9875691500E-4f);
@@ -111,7 +124,7 @@ __device__ __forceinline__ float2 mlp_act2(float2 v) {
     p = __ffma2_rn(p, r, make_float2(5.0000001201E-1f, 5.0000001201E-1f));
     const float2 z = __fmul2_rn(r, r);
     const float2 pl = __ffma2_rn(p, z, r);
-    const float2 t = make_float2(__uint_as_float((uint32_t)((int32_t)n.x + 127) << 23), __uint_as_float((uint32_t)((int32_t)n.y + 127) << 23));
+    const float2 t = make_float2(mlp_pow2_of_magic(tm.x), mlp_pow2_of_magic(tm.y));
     const float2 e = __ffma2_rn(pl, t, __fadd2_rn(t, make_float2(-1.0f, -1.0f)));
     float2 res;
     res.x = v.x < -17.5f ? -1.0f : e.x;
@@ -136,7 +149,7 @@ __device__ __forceinline__ void softmax_seq(const float* l, int n, float* p) {
 }
 
 // post-processing + write-back of one evaluated row: V and the raw policy-head outputs -> softmax priors / GMM parameters ->
-// the tree tables (mode 0) or dense outputs (mode 1).  Shared by k_mlp and k_qmlp.
+// the tree tables (mode 0) or dense outputs (mode 1).  Shared by k_mlp and k_qmlp2; the caller counts the evaluation.
 __device__ __forceinline__ void mlp_finish_row(const MlpParams& p, int gr, int leafw, double lr, float V, const float* raw) {
     float post[3 * AZG_MAX_K];
     int npost;
@@ -170,10 +183,11 @@ __device__ __forceinline__ void mlp_finish_row(const MlpParams& p, int gr, int l
             if (leafw & LEAF_ROOTCHILD) p.et[(size_t)gr * CROOT_MAX_KIDS + ((leafw >> LEAF_J_SHIFT) & 0xFF)].V = V;
             else p.crows[ri].V = V;
             p.ctl[gr].leafR = lr + (double)__fmul_rn(p.gamma_f32, V);
-            float* h = p.chead + ri * p.HS;
-            for (int i = 0; i < npost; ++i) h[i] = post[i];
+            float* h = p.chead + ri * p.HS;  // HS is a multiple of 4 floats: vector stores
+            for (int i = 0; i < npost; i += 4)
+                *reinterpret_cast<float4*>(h + i) = make_float4(post[i], i + 1 < npost ? post[i + 1] : 0.0f, i + 2 < npost ? post[i + 2] : 0.0f,
+                                                                i + 3 < npost ? post[i + 3] : 0.0f);
         }
-        p.evals[gr] += 1;
     }
 }
 
@@ -331,6 +345,7 @@ __device__ __forceinline__ void mlp_unit(const MlpParams& p, const float* w, flo
         float raw[3 * AZG_MAX_K];
         for (int i = 0; i < p.P; ++i) raw[i] = outg[(1 + i) * TU + row];
         mlp_finish_row(p, gr, leafw, lr, outg[row], raw);
+        if (p.mode == 0) p.evals[gr] += 1;
     }
 }
 

@@ -1,0 +1,397 @@
+// qmlp2.cuh -- batched leaf evaluation on the 5th-generation tensor cores, two row tiles in flight per SM.
+//
+// Same arithmetic contract as qmlp.cuh (AZG_FLAG_EVAL_Q8: exact int8-sliced fixed-point products, oracle/azg_oracle.h),
+// different schedule.  ncu on the one-tile-at-a-time kernel (profiles/r1c) showed the SM issuing on 35 % of its cycles: all 16
+// warps walk the same phase, so a third of the samples sit at the CTA barriers, in the wait for the MMAs and behind the four
+// warps that post-process a finished tile.  Here
+//   * a dedicated MMA warp issues every tcgen05.mma; the 16 epilogue warps never issue, they only wait on mbarriers;
+//   * two tiles (A, B) of up to 128 rows are in flight and every epilogue warp alternates between them phase by phase, so
+//     the MMAs of one tile run under the epilogue arithmetic of the other;
+//   * each H x H layer is issued as two N = 64 halves into a 192-column accumulator window per tile (PA | PB | PC, 64
+//     columns each): the epilogue of half 0 overlaps the MMAs of half 1, and two tiles fit the 512 TMEM columns
+//     (2 x 192 + 2 x 64 columns of scratch for the head partial sums);
+//   * the only thread barriers left are 128-thread named barriers among the four warps that share a row group (row maximum,
+//     head partial sums); the tile's post-processing rotates over those four warps;
+//   * the tile is a RUN-TIME index everywhere (one copy of the epilogue code: the first version, specialised per tile and
+//     layer, was 210 KB of SASS and starved on instruction fetch): the 16 activations a thread produces in half 0 wait for
+//     half 1 in the tile's TMEM scratch columns, not in registers.
+// Thread (row r = 32*(warp%4) + lane, cq = warp/4) owns outputs j = 32*cq .. 32*cq+31 of row r in every layer (TMEM lane r is
+// readable by warps with warp%4 == r/32 only).  Half h of a layer produces the outputs j = 32*cq + 16*h + i, i < 16, of every
+// thread: the weight digit planes are stored with their rows permuted (engine.cu pack_weights_q8, qmlp_perm_row) so that
+// those are D columns 16*cq + i of the half, and the 16 activations a thread hands to the next layer are one 16-byte k-chunk
+// (k/16 = 2*cq + h) of the K-major A operand.
+#pragma once
+#include "qmlp.cuh"
+
+#define Q2_EPI_THREADS 512
+#define Q2_THREADS 640                // 16 epilogue warps + the warpgroup of the MMA warp (registers are rebalanced with setmaxnreg)
+#define Q2_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24))  // s8 x s8 -> s32, K-major, N = 64, M = 128
+#define Q2_ACC_COLS 192               // accumulator window of a tile: PA | PB | PC, 64 columns each
+#define Q2_SCRATCH_COL 384            // head partial sums of tile T: columns 384 + 64 T + 16 cq + c
+#define Q2_MAX_PO 16
+
+__host__ __device__ inline size_t qmlp2_smem_bytes(int NL, int qfl_count) {
+    return (size_t)NL * 3 * QMLP_PLANE + 2 * 3 * QMLP_PLANE + (size_t)qfl_count * 4 + 2 * 4 * 128 * 4 + 1024;
+}
+// row of the digit planes that holds output j: half h = (j/16)%2, D column of the half = 16*(j/32) + j%16
+__host__ __device__ inline int qmlp_perm_row(int j) { return 64 * ((j >> 4) & 1) + 16 * (j >> 5) + (j & 15); }
+
+// The shared-memory descriptors of this kernel differ only in their start-address field: the issuing thread keeps 32-bit low
+// words (start address >> 4 | LBO 2048 B) and the MMA assembles the 64-bit operands, so it needs a handful of registers.
+#define Q2_DESC_HI ((128u >> 4) | (1u << 14))  // SBO 128 B, descriptor version 1
+__device__ __forceinline__ uint32_t q2_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((2048u >> 4) << 16); }
+__device__ __forceinline__ void umma_i8_n64(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(da_lo), "r"(db_lo), "r"(Q2_IDESC), "r"(accumulate), "r"(Q2_DESC_HI)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+                   "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+                 "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld4f(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st4f(uint32_t taddr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// per-CTA constants of the epilogue warps
+struct Q2Ctx {
+    const float* W0;     // [S][H] layer-0 weights, k-major
+    const float* b0;     // [H]
+    const float2* cwb;   // [NL][H] (cw[j], bias[j])
+    const float* Wh;     // [H][PO_PAD]
+    const float* bh;     // [PO_PAD]
+    float* pmax;         // [2][4][128]
+    int8_t* sA;          // [2][3][QMLP_PLANE]
+    uint64_t *full, *ready, *freeb;
+    uint32_t tb;         // TMEM base
+    int r, lg, cq;
+};
+
+// row maximum over the four column quarters -> scale -> digits of this thread's two k-chunks -> shared memory -> "ready"
+__device__ __forceinline__ float q2_quantise_store(const Q2Ctx& c, int T, bool wact, const float* a0, const float* a1, float pm) {
+    float cx = 0.0f;
+    if (wact) {
+        float* pmx = c.pmax + T * 512;
+        pmx[c.cq * 128 + c.r] = pm;
+        group_sync(1 + c.lg, 128);
+        const float m = fmaxf(fmaxf(pmx[c.r], pmx[128 + c.r]), fmaxf(pmx[256 + c.r], pmx[384 + c.r]));
+        const int e = q8_exponent(m);
+        const float sx = __uint_as_float((uint32_t)(276 - e) << 23);  // 2^(149-e)
+        cx = __uint_as_float((uint32_t)(e - 22) << 23);               // 2^(e-149)
+        int8_t* sAT = c.sA + T * 3 * QMLP_PLANE;
+        q8_store16(a0, sx, sAT, c.cq * 2, c.r);
+        q8_store16(a1, sx, sAT, c.cq * 2 + 1, c.r);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of A -> visible to the tensor core
+    }
+    mbar_arrive(c.ready + T);
+    return cx;
+}
+
+// layer 0 (S -> H) in FP32 FMA on this thread's 32 outputs, then quantise
+template <int S, int ACT>
+__device__ __forceinline__ float q2_layer0(const Q2Ctx& c, const MlpParams& p, int T, bool wact, int gr, bool valid) {
+    float a[32];
+    float pm = 0.0f;
+    if (wact) {
+        float x[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) x[s] = 0.0f;
+        if (valid) {
+            if (p.xstride == 4) {
+                const float4 v = *reinterpret_cast<const float4*>(p.X + (size_t)gr * 4);
+                x[0] = v.x; x[1] = v.y; x[2] = v.z;
+                if (S > 3) x[S - 1] = v.w;
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; ++s) x[s] = p.X[(size_t)gr * p.xstride + s];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const int j = c.cq * 32 + i;
+            float2 acc = *reinterpret_cast<const float2*>(c.b0 + j);
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc = __ffma2_rn(make_float2(x[s], x[s]), *reinterpret_cast<const float2*>(c.W0 + s * 128 + j), acc);
+            const float2 e = mlp_act2<ACT>(acc);
+            a[i] = e.x; a[i + 1] = e.y;
+            pm = fmaxf(pm, fmaxf(fabsf(e.x), fabsf(e.y)));
+        }
+    }
+    return q2_quantise_store(c, T, wact, a, a + 16, pm);
+}
+
+// heads: partial FMA chains over this thread's 32 activations -> TMEM scratch -> one thread per row sums them and post-processes
+__device__ __forceinline__ void q2_heads(const Q2Ctx& c, const MlpParams& p, int T, const float* a0, const float* a1, bool finisher,
+                                         bool need, int gr, int leafw, double lr, uint32_t& nev, int& ev_row) {
+    const uint32_t lane_base = c.tb + ((uint32_t)(c.lg * 32) << 16) + Q2_SCRATCH_COL + T * 64;
+#pragma unroll 1
+    for (int c4 = 0; c4 < p.PO_PAD / 4; ++c4) {
+        float2 lo = make_float2(0.0f, 0.0f), hi = make_float2(0.0f, 0.0f);
+        const float* wp = c.Wh + (c.cq * 32) * p.PO_PAD + c4 * 4;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + i * p.PO_PAD);
+            const float ai = i < 16 ? a0[i & 15] : a1[i & 15];
+            const float2 av = make_float2(ai, ai);
+            lo = __ffma2_rn(av, make_float2(w4.x, w4.y), lo);
+            hi = __ffma2_rn(av, make_float2(w4.z, w4.w), hi);
+        }
+        tmem_st4f(lane_base + c.cq * 16 + c4 * 4, lo.x, lo.y, hi.x, hi.y);
+    }
+    tmem_wait_st();
+    tc_fence_before();
+    group_sync(1 + c.lg, 128);
+    tc_fence_after();
+    if (finisher) {  // warp-uniform
+        float out[Q2_MAX_PO];
+#pragma unroll 1
+        for (int c4 = 0; c4 < p.PO_PAD / 4; ++c4) {
+            float q0[4], q1[4], q2[4], q3[4];
+            tmem_ld4f(lane_base + c4 * 4, q0);
+            tmem_ld4f(lane_base + 16 + c4 * 4, q1);
+            tmem_ld4f(lane_base + 32 + c4 * 4, q2);
+            tmem_ld4f(lane_base + 48 + c4 * 4, q3);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                out[c4 * 4 + i] = __fadd_rn(__fadd_rn(__fadd_rn(q0[i], q1[i]), __fadd_rn(q2[i], q3[i])), c.bh[c4 * 4 + i]);
+        }
+        if (need) {
+            mlp_finish_row(p, gr, leafw, lr, out[0], out + 1);
+            ++nev;
+            ev_row = gr;
+        }
+    }
+}
+
+template <int S, int ACT, int NL>
+__global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
+    extern __shared__ __align__(1024) uint8_t qsm_raw[];
+    __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2];
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* qsm = reinterpret_cast<uint8_t*>(((uintptr_t)qsm_raw + 1023) & ~(uintptr_t)1023);
+    int8_t* sB = reinterpret_cast<int8_t*>(qsm);                     // [NL][3][8][128][16], rows permuted
+    int8_t* sA = sB + (size_t)NL * 3 * QMLP_PLANE;                   // [2][3][8][128][16]
+    float* fl = reinterpret_cast<float*>(sA + 2 * 3 * QMLP_PLANE);   // W0t[S][H], b0[H], NL x (cw, bias)[H], Wh[H][PO_PAD], bh[PO_PAD]
+    float* pmax = fl + p.qfl_count;                                  // [2][4][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // this CTA's contiguous row range, cut into an even number of equal tiles of at most 128 rows
+    const int per = (p.n + gridDim.x - 1) / gridDim.x;
+    const int row_begin = blockIdx.x * per;
+    const int row_end = min(row_begin + per, p.n);
+    if (row_begin >= row_end) return;
+    const int nrows = row_end - row_begin;
+    int ntiles = (nrows + 127) / 128;
+    if (ntiles > 1) ntiles = (ntiles + 1) & ~1;
+    const int th = (nrows + ntiles - 1) / ntiles;
+
+    if (tid == 0) {
+        mbar_init(&wbar, 1);
+        for (int T = 0; T < 2; ++T) {
+            mbar_init(&full[T], 1);
+            mbar_init(&ready[T], Q2_EPI_THREADS);
+            mbar_init(&freeb[T], Q2_EPI_THREADS);
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t bytesB = (uint32_t)NL * 3 * QMLP_PLANE, bytesF = (uint32_t)p.qfl_count * 4u;
+        mbar_expect_tx(&wbar, bytesB + bytesF);
+        for (uint32_t o = 0; o < bytesB; o += 32768u) bulk_g2s(sB + o, p.qdigits + o, min(32768u, bytesB - o), &wbar);
+        bulk_g2s(fl, p.qfl, bytesF, &wbar);
+    }
+    mbar_wait(&wbar, 0);
+
+    if (warp >= 16) {
+        // ---- MMA warpgroup: gives its registers to the epilogue warps; one thread issues, in the order the epilogue warps consume
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == 16 && lane == 0) {
+            uint32_t rph = 0, fph = 0;  // bit T: parity of the next wait on ready[T] / freeb[T]
+            for (int t0 = 0; t0 < ntiles; t0 += 2) {
+                const int nt = min(2, ntiles - t0);
+#pragma unroll 1
+                for (int l = 0; l < NL; ++l) {
+#pragma unroll 1
+                    for (int hT = 0; hT < 2 * nt; ++hT) {
+                        const int h = hT >> (nt - 1), T = hT & (nt - 1);  // nt is 1 or 2
+                        if (h == 0) { mbar_wait(&ready[T], (rph >> T) & 1u); rph ^= 1u << T; }
+                        else { mbar_wait(&freeb[T], (fph >> T) & 1u); fph ^= 1u << T; }
+                        tc_fence_after();
+                        // low descriptor words: +1024 per digit plane (16 KB), +256 per k-step of 32 (4 KB)
+                        const uint32_t aH = q2_desc_lo(smem_u32(sA) + (uint32_t)T * 3 * QMLP_PLANE), aM = aH + 1024, aL = aH + 2048;
+                        const uint32_t bH = q2_desc_lo(smem_u32(sB) + (uint32_t)l * 3 * QMLP_PLANE + (uint32_t)h * 1024u), bM = bH + 1024, bL = bH + 2048;
+                        const uint32_t acc = tb + T * Q2_ACC_COLS;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_i8_n64(acc, aH + k * 256, bH + k * 256, k > 0);        // PA = xh*wh
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_i8_n64(acc + 64, aH + k * 256, bM + k * 256, k > 0);   // PB = xh*wm
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_i8_n64(acc + 64, aM + k * 256, bH + k * 256, 1);       //    + xm*wh
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_i8_n64(acc + 128, aH + k * 256, bL + k * 256, k > 0);  // PC = xh*wl
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_i8_n64(acc + 128, aM + k * 256, bM + k * 256, 1);      //    + xm*wm
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_i8_n64(acc + 128, aL + k * 256, bH + k * 256, 1);      //    + xl*wh
+                        umma_commit(&full[T]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- epilogue warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");  // 512 x 112 + 128 x 24 <= 640 x 96, the CTA's pool at launch
+        Q2Ctx c;
+        c.W0 = fl;
+        c.b0 = fl + S * 128;
+        c.cwb = reinterpret_cast<const float2*>(fl + S * 128 + 128);
+        c.Wh = fl + S * 128 + 128 + NL * 2 * 128;
+        c.bh = c.Wh + 128 * p.PO_PAD;
+        c.pmax = pmax;
+        c.sA = sA;
+        c.full = full; c.ready = ready; c.freeb = freeb;
+        c.tb = tb;
+        c.lg = warp & 3; c.cq = warp >> 2;
+        c.r = c.lg * 32 + lane;
+        uint32_t fullph = 0;  // bit T: parity of the next wait on full[T]
+        uint32_t nev = 0;     // rows this thread post-processed; added to the per-tree evaluation counters once, at the end
+        int ev_row = 0;
+#pragma unroll 1
+        for (int t0 = 0; t0 < ntiles; t0 += 2) {
+            const int nt = min(2, ntiles - t0);
+            // per-slot state (slot T holds tile t0 + T): scale of the layer input, and for the rows this thread post-processes
+            // the leaf word / reward (needed only when the tile is finished; loaded here so the latency is hidden)
+            float cx0 = 0.0f, cx1 = 0.0f;
+            int leafw0 = 0, leafw1 = 0;
+            double lr0 = 0.0, lr1 = 0.0;
+            bool need0 = false, need1 = false;
+#pragma unroll 1
+            for (int T = 0; T < nt; ++T) {
+                const int row0 = row_begin + (t0 + T) * th;
+                const int nv = max(0, min(th, row_end - row0));
+                const bool wact = c.lg * 32 < nv, valid = c.r < nv;
+                const int gr = row0 + c.r;
+                bool need = valid && c.cq == ((t0 + T) & 3);
+                int leafw = 0;
+                double lr = 0.0;
+                if (need && p.mode == 0) {
+                    if (p.variant == 1) {
+                        const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
+                        const uint4 c0 = cp[0], c1 = cp[1];
+                        leafw = (int)c0.z;
+                        lr = __hiloint2double((int)c1.w, (int)c1.z);
+                    } else {
+                        leafw = p.leaf[gr];
+                    }
+                    need = (leafw & LEAF_EVAL) != 0;
+                }
+                const float cx = q2_layer0<S, ACT>(c, p, T, wact, gr, valid);
+                if (T == 0) { cx0 = cx; leafw0 = leafw; lr0 = lr; need0 = need; }
+                else { cx1 = cx; leafw1 = leafw; lr1 = lr; need1 = need; }
+            }
+#pragma unroll 1
+            for (int step = 0; step < NL * 2 * nt; ++step) {
+                // step -> (layer, half, tile), tile fastest; nt is 1 or 2
+                const int sh = nt - 1, T = step & sh, h = (step >> sh) & 1, l = step >> (sh + 1);
+                const int row0 = row_begin + (t0 + T) * th;
+                const int nv = max(0, min(th, row_end - row0));
+                const bool wact = c.lg * 32 < nv;
+                const float cx = T ? cx1 : cx0;
+                mbar_wait(full + T, (fullph >> T) & 1u);
+                fullph ^= 1u << T;
+                tc_fence_after();
+                const uint32_t lane_base = tb + ((uint32_t)(c.lg * 32) << 16);
+                const uint32_t stash = lane_base + Q2_SCRATCH_COL + T * 64 + c.cq * 16;
+                float v[16];
+                float pm = 0.0f;
+                if (wact) {
+                    const float2* cb = c.cwb + l * 128 + c.cq * 32 + 16 * h;
+                    const uint32_t ta = lane_base + T * Q2_ACC_COLS + c.cq * 16;
+                    int32_t pa[16], pb[16], pc[16];
+                    tmem_ld16(ta, pa);
+                    tmem_ld16(ta + 64, pb);
+                    tmem_ld16(ta + 128, pc);
+                    tmem_wait_ld();
+                    tc_fence_before();
+                    if (h == 0) mbar_arrive(freeb + T);  // the window may be overwritten by the MMAs of half 1
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float4 sb = *reinterpret_cast<const float4*>(cb + i);  // (cw, bias) of outputs i, i+1
+                        float u0 = __fmaf_rn(q8_i2f_22(pa[i]), 256.0f, q8_i2f_22(pb[i]));
+                        float u1 = __fmaf_rn(q8_i2f_22(pa[i + 1]), 256.0f, q8_i2f_22(pb[i + 1]));
+                        u0 = __fmaf_rn(u0, 256.0f, q8_i2f_23(pc[i]));
+                        u1 = __fmaf_rn(u1, 256.0f, q8_i2f_23(pc[i + 1]));
+                        const float2 y = make_float2(__fmaf_rn(u0, __fmul_rn(cx, sb.x), sb.y), __fmaf_rn(u1, __fmul_rn(cx, sb.z), sb.w));
+                        const float2 ev = mlp_act2<ACT>(y);
+                        v[i] = ev.x; v[i + 1] = ev.y;
+                        pm = fmaxf(pm, fmaxf(fabsf(ev.x), fabsf(ev.y)));
+                    }
+                } else {
+                    tc_fence_before();
+                    if (h == 0) mbar_arrive(freeb + T);
+                }
+                if (h == 0) {
+                    if (wact) {  // park the first 16 activations until half 1 is done (only this thread reads them back)
+                        tmem_st16f(stash, v);
+                        tmem_wait_st();
+                    }
+                } else {
+                    float u[16];
+                    if (wact) {
+                        tmem_ld16f(stash, u);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) pm = fmaxf(pm, fmaxf(fabsf(u[i]), fabsf(u[i + 1])));
+                    }
+                    if (l + 1 < NL) {
+                        const float ncx = q2_quantise_store(c, T, wact, u, v, pm);
+                        if (T) cx1 = ncx; else cx0 = ncx;
+                    } else if (wact) {
+                        q2_heads(c, p, T, u, v, c.cq == ((t0 + T) & 3), T ? need1 : need0, row0 + c.r, T ? leafw1 : leafw0, T ? lr1 : lr0, nev, ev_row);
+                    }
+                }
+            }
+        }
+        if (nev && p.mode == 0) p.evals[ev_row] += nev;  // only the total over trees is reported (azg_get_counters)
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "n"(512) : "memory");
+}
