@@ -22,7 +22,8 @@ EXPORTS = [
     "azg_create", "azg_destroy", "azg_last_error", "azg_version", "azg_num_weights", "azg_set_weights",
     "azg_search_discrete", "azg_search_continuous", "azg_cmax", "azg_root_results", "azg_search_host", "azg_status",
     "azg_rows", "azg_set_tapes", "azg_dump_tree_discrete", "azg_dump_tree_continuous", "azg_get_counters",
-    "azg_head_dim", "azg_mlp_forward", "azg_env_step", "azg_profile_search",
+    "azg_head_dim", "azg_mlp_forward", "azg_env_step", "azg_profile_search", "azg_set_seed", "azg_selfplay_seed",
+    "azg_selfplay_step",
 ]
 
 
@@ -44,6 +45,12 @@ class DumpDiscrete(C.Structure):
 
 class DumpContinuous(C.Structure):
     FIELDS = ("n_rows", "parent", "action", "eW", "en", "expanded", "node_n", "terminal", "V", "r", "state", "head")
+    _fields_ = [(n, C.c_void_p) for n in FIELDS]
+
+
+class SelfPlayIO(C.Structure):
+    FIELDS = ("d_env_state", "d_ep_step", "d_episode", "d_root_n", "d_obs", "d_actions", "d_counts", "d_Q", "d_V_target",
+              "d_n_children", "d_action_taken", "d_reward", "d_done")
     _fields_ = [(n, C.c_void_p) for n in FIELDS]
 
 
@@ -90,6 +97,10 @@ def load():
     L.azg_head_dim.restype, L.azg_head_dim.argtypes = i32, [vp]
     L.azg_mlp_forward.restype, L.azg_mlp_forward.argtypes = C.c_int, [vp, i32, vp, vp, vp, vp]
     L.azg_env_step.restype, L.azg_env_step.argtypes = C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.azg_set_seed.restype, L.azg_set_seed.argtypes = C.c_int, [vp, C.c_uint64, vp]
+    L.azg_selfplay_seed.restype, L.azg_selfplay_seed.argtypes = C.c_uint64, [C.c_uint64, i64]
+    L.azg_selfplay_step.restype = C.c_int
+    L.azg_selfplay_step.argtypes = [vp, i32, C.POINTER(SelfPlayIO), i32, i64, i64, C.c_uint64, i32, i32, i32, C.c_double, vp]
     _lib = L
     return L
 

@@ -95,7 +95,7 @@ struct TreeParams {
     int32_t puct_f32, v_target, use_tape;
     double c_uct, gamma, epsilon;
     float gamma_f32, action_bound;
-    uint64_t seed;
+    const uint64_t* seedp;  // Philox key, read from device memory so that azg_set_seed re-keys a captured graph
     int64_t tree_id0;
     // discrete tables
     DRow* drows;      // [B][R]
@@ -154,7 +154,7 @@ __device__ __forceinline__ u32x4 rng_block(uint64_t seed, int64_t tree, int stre
 
 // stream 0: random.random() / random.choice / random.randint replacements (helpers.py:51, mcts.py:190-192)
 __device__ __forceinline__ uint32_t rng_select_u32(const TreeParams& p, int64_t tree, int draw) {
-    return rng_block(p.seed, tree, 0, draw, 0).x;
+    return rng_block(__ldg(p.seedp), tree, 0, draw, 0).x;
 }
 __device__ __forceinline__ float u32_to_unit(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 __device__ __forceinline__ int u32_to_index(uint32_t x, int n) { return (int)__umulhi(x, (uint32_t)n); }

@@ -20,6 +20,7 @@
 #include "mlp.cuh"
 #include "qmlp.cuh"
 #include "qmlp2.cuh"
+#include "selfplay.cuh"
 #include "tree_continuous.cuh"
 #include "tree_discrete.cuh"
 
@@ -58,6 +59,7 @@ struct azg_engine {
     int32_t* root_n_init = nullptr;
     int32_t* err = nullptr;
     float* wpack = nullptr;
+    uint64_t* d_seed = nullptr;  // Philox key read by the kernels (azg_set_seed)
     // AZG_FLAG_EVAL_Q8: int8 digit planes + f32 side table of the tensor-core evaluation kernel (qmlp.cuh)
     int8_t* qdigits = nullptr;
     float* qfl = nullptr;
@@ -104,7 +106,7 @@ extern "C" void azg_destroy(azg_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     void* ptrs[] = {e->drows, e->dstate, e->crows, e->et, e->ctl, e->chead, e->pw_table, e->n_rows, e->draws,
-                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->qdigits, e->qfl, e->r_actions,
+                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->qdigits, e->qfl, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -212,6 +214,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(root_n_init, B);
     ALLOC(err, 1);
     ALLOC(wpack, (size_t)e->wcount);
+    ALLOC(d_seed, 1);
     if (e->q8) {
         ALLOC(qdigits, (size_t)(c.n_hidden - 1) * 3 * QMLP_PLANE);
         ALLOC(qfl, (size_t)e->qfl_count);
@@ -219,6 +222,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(r_actions, B * e->cmax); ALLOC(r_counts, B * e->cmax); ALLOC(r_Q, B * e->cmax); ALLOC(r_Vt, B); ALLOC(r_nchild, B);
 #undef ALLOC
     CK(cudaMemset(e->err, 0, sizeof(int32_t)));
+    CK(cudaMemcpy(e->d_seed, &c.seed, sizeof(uint64_t), cudaMemcpyHostToDevice));
     CK(cudaMemset(e->n_rows, 0, B * sizeof(int32_t)));
     CK(cudaMemset(e->ctr, 0, 4 * B * sizeof(uint32_t)));
     {
@@ -375,7 +379,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.puct_f32 = c.puct_f32; p.v_target = c.v_target; p.use_tape = e->tapeV != nullptr;
     p.c_uct = c.c_uct; p.gamma = c.gamma; p.epsilon = c.epsilon;
     p.gamma_f32 = (float)c.gamma; p.action_bound = c.action_bound;
-    p.seed = c.seed; p.tree_id0 = tree_id0;
+    p.seedp = e->d_seed; p.tree_id0 = tree_id0;
     p.drows = e->drows; p.dstate = e->dstate;
     p.crows = e->crows; p.et = e->et; p.ctl = e->ctl; p.chead = e->chead;
     p.pw_table = e->pw_table;
@@ -712,6 +716,52 @@ extern "C" int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]) {
     }
     out[0] = (int64_t)nb * e->last_N;
     out[7] = e->launches;
+    return AZG_OK;
+}
+
+extern "C" int azg_set_seed(azg_engine* e, uint64_t seed, void* stream) {
+    if (!e) return fail(AZG_EINVAL, "null engine");
+    CK(cudaSetDevice(e->cfg.device));
+    k_set_seed<<<1, 1, 0, (cudaStream_t)stream>>>(e->d_seed, seed);
+    CK(cudaGetLastError());
+    e->cfg.seed = seed;
+    return AZG_OK;
+}
+
+extern "C" uint64_t azg_selfplay_seed(uint64_t seed, int64_t step_index) { return seed + (uint64_t)step_index * 0x9E3779B97F4A7C15ull; }
+
+// One self-play step of B environments: re-key -> search -> root results (the replay row) -> final action -> real env step ->
+// episode bookkeeping (selfplay.cuh).  Everything is enqueued on `stream`; nothing synchronises.
+extern "C" int azg_selfplay_step(azg_engine* e, int32_t B, const azg_selfplay_io* io, int32_t n_rollouts, int64_t tree_id0,
+                                 int64_t step_index, uint64_t base_seed, int32_t max_episode_length, int32_t deterministic,
+                                 int32_t by_value, double temperature, void* stream) {
+    if (!e || !io) return fail(AZG_EINVAL, "null argument");
+    if (!io->d_env_state || !io->d_ep_step || !io->d_episode || !io->d_obs || !io->d_actions || !io->d_counts || !io->d_Q ||
+        !io->d_V_target || !io->d_n_children || !io->d_action_taken || !io->d_reward || !io->d_done)
+        return fail(AZG_EINVAL, "null buffer in azg_selfplay_io");
+    const bool disc = e->cfg.variant == AZG_DISCRETE;
+    if (disc && !io->d_root_n) return fail(AZG_EINVAL, "d_root_n is required for the discrete variant");
+    if (max_episode_length < 1) return fail(AZG_EINVAL, "max_episode_length must be >= 1");
+    if (!(temperature > 0.0)) return fail(AZG_EINVAL, "temperature must be > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = azg_set_seed(e, azg_selfplay_seed(base_seed, step_index), stream);
+    if (rc) return rc;
+    rc = run_search(e, B, io->d_env_state, disc ? io->d_root_n : nullptr, n_rollouts, tree_id0, st);
+    if (rc) return rc;
+    rc = azg_root_results(e, B, io->d_actions, io->d_counts, io->d_Q, io->d_V_target, io->d_n_children, stream);
+    if (rc) return rc;
+    SelfPlayParams sp;
+    memset(&sp, 0, sizeof sp);
+    sp.B = B; sp.cmax = e->cmax; sp.max_episode_length = max_episode_length; sp.deterministic = deterministic; sp.by_value = by_value;
+    sp.temperature = temperature; sp.tree_id0 = tree_id0; sp.seedp = e->d_seed;
+    sp.env_state = io->d_env_state; sp.ep_step = io->d_ep_step; sp.episode = io->d_episode; sp.root_n = io->d_root_n;
+    sp.actions = io->d_actions; sp.counts = io->d_counts; sp.Q = io->d_Q; sp.n_children = io->d_n_children;
+    sp.obs = io->d_obs; sp.action_taken = io->d_action_taken; sp.reward = io->d_reward; sp.done = io->d_done;
+    sp.drows = e->drows; sp.R = e->R;
+    const int tb = 128, tg = (B + tb - 1) / tb;
+    if (disc) k_selfplay_discrete<<<tg, tb, 0, st>>>(sp);
+    else k_selfplay_continuous<<<tg, tb, 0, st>>>(sp);
+    CK(cudaGetLastError());
     return AZG_OK;
 }
 

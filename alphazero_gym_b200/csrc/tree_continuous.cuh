@@ -83,9 +83,10 @@ __device__ __forceinline__ void set_list_byte(uint32_t w[4], int j, int val) {
 
 // stream 1: noise of the j-th widening insert of `tree`: component uniform + K standard normals
 __device__ __forceinline__ void pw_noise(const TreeParams& p, int64_t tree, int j, float& u, float* z) {
-    u = u32_to_unit(rng_block(p.seed, tree, 1, j, 0).x);
+    const uint64_t seed = __ldg(p.seedp);
+    u = u32_to_unit(rng_block(seed, tree, 1, j, 0).x);
     for (int b = 0; 2 * b < p.K; ++b) {
-        const u32x4 c = rng_block(p.seed, tree, 1, j, 1 + b);
+        const u32x4 c = rng_block(seed, tree, 1, j, 1 + b);
         const double u1 = ((double)c.x + 0.5) * 2.3283064365386963e-10;
         const double u2 = ((double)c.y + 0.5) * 2.3283064365386963e-10;
         const double rad = sqrt(-2.0 * det::log_(u1));

@@ -109,6 +109,43 @@ int azg_search_host(azg_engine* e, int32_t B, const double* h_root_state, const 
 /* Device status of the last search(es): AZG_OK, AZG_ENAN or AZG_ECAPACITY.  Synchronises `stream`. */
 int azg_status(azg_engine* e, void* stream);
 
+/* Re-key the Philox streams (tie-break / eps-greedy / action noise / self-play draws).  Stream-ordered: searches enqueued
+ * after the call use the new key, also when they replay a captured CUDA graph.  The reference seeds once per run
+ * (run_continuous.py:24-25, run_discrete.py:27-28). */
+int azg_set_seed(azg_engine* e, uint64_t seed, void* stream);
+
+/* ---- self-play step (BASELINE config 5) -------------------------------------------------------------
+ * One environment step of B independent self-play environments, the body of the reference's episode loop
+ * (run_continuous.py:117-142, run_discrete.py:100-122), batched and entirely on the device:
+ *   re-key (key = azg_selfplay_seed(base_seed, step_index)) -> search from d_env_state -> root results, written to the
+ *   replay-row buffers (buffer.store((s, actions, counts, Qs, V)), buffers.py:61) -> final action:
+ *     continuous  actions[counts.argmax()] (agents.py:533; by_value: Qs.argmax());
+ *     discrete    pi = stable_normalizer(counts | Qs, temperature) (helpers.py:9-27), pi.argmax() if deterministic else a
+ *                 draw with np.random.choice's inverse-CDF rule (agents.py:294-301);
+ *   -> the real Env.step -> if terminal or the episode reached max_episode_length: Env.reset() and a fresh tree
+ *   (reset_mcts), else discrete tree reuse: d_root_n = visit count of the chosen child (mcts.py:495-526).
+ * All pointers are device pointers owned by the caller; in/out arrays carry the state from step to step. */
+typedef struct azg_selfplay_io {
+    double* d_env_state;   /* in/out [B][4|2] hidden env state (CartPole x, x_dot, theta, theta_dot | Pendulum th, thdot) */
+    int32_t* d_ep_step;    /* in/out [B] steps taken in the current episode */
+    int32_t* d_episode;    /* in/out [B] episode counter (indexes the reset stream) */
+    int32_t* d_root_n;     /* in/out [B] discrete only: root visit count carried into the next search; NULL for continuous */
+    float* d_obs;          /* out [B][state_dim] observation the search started from (the replay row's s) */
+    float* d_actions;      /* out [B][cmax] */
+    int32_t* d_counts;     /* out [B][cmax] */
+    double* d_Q;           /* out [B][cmax] */
+    double* d_V_target;    /* out [B] */
+    int32_t* d_n_children; /* out [B] */
+    float* d_action_taken; /* out [B] */
+    double* d_reward;      /* out [B] raw env reward of the real step */
+    int32_t* d_done;       /* out [B] 1 if the episode ended with this step */
+} azg_selfplay_io;
+
+uint64_t azg_selfplay_seed(uint64_t base_seed, int64_t step_index);
+int azg_selfplay_step(azg_engine* e, int32_t B, const azg_selfplay_io* io, int32_t n_rollouts, int64_t tree_id0,
+                      int64_t step_index, uint64_t base_seed, int32_t max_episode_length, int32_t deterministic,
+                      int32_t by_value, double temperature, void* stream);
+
 /* ---- parity hooks: evaluator injection and full tree dump -------------------------------- */
 /* Tapes are device arrays indexed by tree and by node/row creation index, stride azg_rows(e):
  * V [B][R]; prior [B][R][A] (discrete); action [B][R] (continuous).  Passing d_V = NULL returns to the

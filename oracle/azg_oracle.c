@@ -525,6 +525,12 @@ int azo_env_step(const azo_config* c, const double* s_in, float action, double* 
     return term;
 }
 
+/* observation of a hidden env state: CartPole the state itself (f32), Pendulum (cos th, sin th, thdot) */
+void azo_obs(const azo_config* c, const double* s, float* obs) {
+    if (c->variant == AZO_DISCRETE) for (int i = 0; i < 4; ++i) obs[i] = (float)s[i];
+    else pendulum_obs(c, s, obs);
+}
+
 int32_t azo_pw_limit(double c_pw, double kappa, int32_t n) { return (int32_t)ceil(c_pw * pow((double)(n + 1), kappa)); }
 
 /* ------------------------------------------------------------------------------------------------

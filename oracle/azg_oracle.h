@@ -175,6 +175,7 @@ void azo_mlp_forward(const azo_config* cfg, const float* weights, int32_t n, con
 void azo_head_post(const azo_config* cfg, const float* raw, float* out);
 float azo_sample_action(const azo_config* cfg, const float* head, float u_comp, const float* z);
 int azo_env_step(const azo_config* cfg, const double* s_in, float action, double* s_out, double* reward, float* obs);
+void azo_obs(const azo_config* cfg, const double* s, float* obs); /* observation of a hidden env state */
 
 float azo_det_expf(float x);
 float azo_det_expm1f(float x);

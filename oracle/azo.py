@@ -89,6 +89,8 @@ def lib():
         L.azo_head_post.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_void_p]
         L.azo_sample_action.restype = C.c_float
         L.azo_sample_action.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_float, C.c_void_p]
+        L.azo_obs.restype = None
+        L.azo_obs.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_void_p]
         L.azo_env_step.restype = C.c_int
         L.azo_env_step.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_float, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
         for n in ("expf", "expm1f", "tanhf"):
@@ -260,6 +262,13 @@ def env_step(cfg: Config, state: np.ndarray, action: float):
     r = C.c_double()
     term = lib().azo_env_step(C.byref(cfg.c()), _p(s), C.c_float(action), _p(o), C.byref(r), _p(obs))
     return o, r.value, bool(term), obs
+
+
+def obs(cfg: Config, state: np.ndarray) -> np.ndarray:
+    s = np.ascontiguousarray(state, np.float64)
+    o = np.zeros(cfg.state_dim, np.float32)
+    lib().azo_obs(C.byref(cfg.c()), _p(s), _p(o))
+    return o
 
 
 def rng_u32(seed: int, tree: int, stream: int, idx: int, block: int = 0, word: int = 0) -> int:
