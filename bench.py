@@ -43,7 +43,12 @@ WORKLOADS = {
     "cartpole_4096x50": ("discrete", 4096, 50),
     "pendulum_32768x200": ("continuous", 32768, 200),
     "pendulum_1024x25": ("continuous", 1024, 25),  # quick sanity size
+    # BASELINE.json configs[4]: self-play loop, 32768 Pendulum environments per GPU (262144 on 8 GPUs) x 200 sims per env step,
+    # weight broadcast every SELFPLAY_BROADCAST_EVERY steps, replay rows all-gathered every step
+    "selfplay_pendulum_32768x200": ("continuous", 32768, 200),
+    "selfplay_pendulum_2048x25": ("continuous", 2048, 25),  # quick sanity size
 }
+SELFPLAY_BROADCAST_EVERY = 4
 FLOP_PER_EVAL = {"discrete": 2 * 17280, "continuous": 2 * 34048}
 
 
@@ -125,12 +130,13 @@ class ClockSampler:
 
 
 def measured_peaks():
+    """(HBM GB/s, SM max MHz, dense bf16 TFLOP/s burst, source)"""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), d.get("bf16_tflops", 1650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, 1650.0, "fallback (B200_PROFILING.md)"
 
 
 def algorithmic_bytes(variant: str, c: dict) -> float:
@@ -201,8 +207,8 @@ def main():
     ap.add_argument("--workload", default="pendulum_65536x100", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--eval", default="fp32", choices=["fp32", "q8"],
-                    help="leaf evaluation arithmetic: FP32 FMA (mlp.cuh) or int8-sliced tcgen05 products (qmlp.cuh)")
+    ap.add_argument("--eval", default="q8", choices=["fp32", "q8"],
+                    help="leaf evaluation arithmetic: int8-sliced tcgen05 products (qmlp2.cuh, default) or FP32 FMA (mlp.cuh)")
     args = ap.parse_args()
     variant, B, N = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -235,46 +241,90 @@ def main():
     eng.set_weights(weights)
     roots_d = torch.from_numpy(roots_h).cuda()
 
+    selfplay = args.workload.startswith("selfplay")
+    api = "azg_search_host via SearchEngine.search_host (wall clock between syncs)"
+    if selfplay:
+        # ---- self-play loop (BASELINE config 5): search -> final action -> real env step, replay rows all-gathered every
+        # step (C2), weights re-broadcast from rank 0 and re-loaded every SELFPLAY_BROADCAST_EVERY steps (C1)
+        from alphazero_gym_b200.selfplay import DeviceReplayBuffer, ROW_KEYS, SelfPlayDriver
+        drv = SelfPlayDriver(eng, B, N, max_episode_length=200, tree_id0=tree_id0, total_envs=B * world, seed=34)
+        replay = DeviceReplayBuffer(max_size=2 * B * world, batch_size=256, obs_dim=3 if variant == "continuous" else 4,
+                                    cmax=eng.cmax, device=eng.device)
+        wflat = torch.from_numpy(weights).cuda()
+        w_pinned = torch.from_numpy(weights).pin_memory()
+        rows_pinned = {k: torch.empty_like(drv.t[k], device="cpu").pin_memory() for k in ROW_KEYS}
+
+        def device_step(i):
+            if i % SELFPLAY_BROADCAST_EVERY == 0:
+                drv.sync_weights(wflat)
+            drv.step(store=False)
+            replay.store(drv.gathered_rows())
+
+        def host_step(i):
+            if i % SELFPLAY_BROADCAST_EVERY == 0:
+                wflat.copy_(w_pinned, non_blocking=True)  # the trainer's new weights arrive from the host
+                drv.sync_weights(wflat)
+            drv.step(store=False)
+            replay.store(drv.gathered_rows())
+            for k in ROW_KEYS:  # this step's replay rows leave for a host-side consumer
+                rows_pinned[k].copy_(drv.t[k], non_blocking=True)
+            torch.cuda.synchronize()
+
+        api = "SelfPlayDriver.step (azg_selfplay_step) + per-step D2H of the replay rows, H2D of the weights at broadcast steps"
+        h2d = weights.nbytes / SELFPLAY_BROADCAST_EVERY
+        d2h = sum(rows_pinned[k].numel() * rows_pinned[k].element_size() for k in ROW_KEYS)
+        extra_launches = 2  # root results + the self-play kernel (+ set_seed)
+    else:
+        def device_step(i):
+            eng.search(roots_d, N, tree_id0=tree_id0)
+            return eng.root_results()
+
+        def host_step(i):
+            return eng.search_host(roots_h, N, tree_id0=tree_id0)
+
+        h2d = roots_h.nbytes
+        extra_launches = 1  # the root-results kernel
+
     # ---- device-resident throughput ("value") ---------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        eng.search(roots_d, N, tree_id0=tree_id0)
-        res = eng.root_results()
+    for i in range(max(args.warmup, 3)):
+        device_step(i)
     eng.status()
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        eng.search(roots_d, N, tree_id0=tree_id0)
-        res = eng.root_results()
+    for i in range(args.steps):
+        device_step(i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     eng.status()
     counters = eng.counters()
-    launches_per_step = counters["launches"] + 1  # + the root-results kernel
+    launches_per_step = counters["launches"] + extra_launches
 
-    # ---- end to end through the host-buffer C-ABI entry point ("e2e") -------------------------------
-    for _ in range(2):
-        out = eng.search_host(roots_h, N, tree_id0=tree_id0)
+    # ---- end to end through the host-facing entry point ("e2e") -------------------------------------
+    for i in range(2):
+        out = host_step(i)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = eng.search_host(roots_h, N, tree_id0=tree_id0)
+    for i in range(args.steps):
+        out = host_step(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
-    checksum = int(out["counts"].sum())
+    checksum = int(drv.t["counts"].sum()) if selfplay else int(out["counts"].sum())
     assert checksum == B * N, f"visit counts do not add up: {checksum} != {B * N}"
-    h2d = roots_h.nbytes
-    d2h = sum(out[k].nbytes for k in ("actions", "counts", "Q", "V_target", "n_children"))
+    if selfplay:
+        roots_d = drv.env_state.clone()
+    else:
+        d2h = sum(out[k].nbytes for k in ("actions", "counts", "Q", "V_target", "n_children"))
 
     # ---- per-kernel times, live, for the roofline ----------------------------------------------------
     eng.profile_search(roots_d, N, tree_id0=tree_id0)
     prof = eng.profile_search(roots_d, N, tree_id0=tree_id0)
     pc = eng.counters()
-    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    hbm_peak, sm_max_mhz, bf16_peak, peak_src = measured_peaks()
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
     ev, tr = prof["evaluation"], prof["tree_step"]
     fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
@@ -288,11 +338,24 @@ def main():
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(args.workload, {})
-    roof_eval = {"kernel": "k_mlp (leaf evaluation)", "bound": "fp32", "achieved": ev_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                 "frac": ev_tflops / fp32_peak, "traffic": traffic.get("k_mlp"),
-                 "peak_source": f"{sm_count} SMs x 128 FMA/clk x 2 x {sm_max_mhz:.0f} MHz (CUDA-core FP32; the 1e-5 parity tolerance rules out TF32/BF16 tensor products)",
-                 "avg_launch_ms": ev_avg_ms, "launches": ev["launches"], "flop_per_launch": FLOP_PER_EVAL[variant] * B,
-                 "share_of_step": ev["ms"] / (ev["ms"] + tr["ms"] + prof["setup"]["ms"])}
+    ev_share = ev["ms"] / (ev["ms"] + tr["ms"] + prof["setup"]["ms"])
+    if args.eval == "q8":
+        # tensor-core evaluation: algorithmic FLOPs (2 x MACs of the network) against the measured dense bf16 peak.
+        # The exact fixed-point arithmetic issues 6 int8 MMAs per algorithmic H x H product, and the kernel is bound by its
+        # CUDA-core epilogue (dequantise, activation, quantise), not by the tensor pipe -- DESIGN.md section 4.2.
+        hh = 2 * 128 * 128 * ((3 if variant == "continuous" else 2) - 1)
+        roof_eval = {"kernel": "k_qmlp2 (leaf evaluation, tcgen05 kind::i8)", "bound": "tensor", "achieved": ev_tflops, "peak": bf16_peak,
+                     "unit": "TFLOP/s", "frac": ev_tflops / bf16_peak, "traffic": traffic.get("k_qmlp2"),
+                     "peak_source": peak_src + " dense bf16; int8 digits: 6 MMAs per algorithmic product",
+                     "avg_launch_ms": ev_avg_ms, "launches": ev["launches"], "flop_per_launch": FLOP_PER_EVAL[variant] * B,
+                     "tensor_ops_issued_per_launch": 6 * hh * B, "tensor_tops_issued": 6 * hh * B / (ev_avg_ms * 1e-3) / 1e12,
+                     "frac_of_fp32_cuda_core_peak": ev_tflops / fp32_peak, "share_of_step": ev_share}
+    else:
+        roof_eval = {"kernel": "k_mlp (leaf evaluation)", "bound": "fp32", "achieved": ev_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                     "frac": ev_tflops / fp32_peak, "traffic": traffic.get("k_mlp"),
+                     "peak_source": f"{sm_count} SMs x 128 FMA/clk x 2 x {sm_max_mhz:.0f} MHz (CUDA-core FP32)",
+                     "avg_launch_ms": ev_avg_ms, "launches": ev["launches"], "flop_per_launch": FLOP_PER_EVAL[variant] * B,
+                     "share_of_step": ev_share}
     roof_tree = {"kernel": "k_step (backup + select + expansion/env step)", "bound": "hbm", "achieved": tr_gbs, "peak": hbm_peak,
                  "unit": "GB/s", "frac": tr_gbs / hbm_peak, "traffic": traffic.get("k_step"), "peak_source": peak_src,
                  "avg_launch_ms": tr_avg_ms, "launches": tr["launches"], "algorithmic_bytes_per_launch": tr_bytes,
@@ -305,6 +368,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, sample = cpu_port_throughput(variant, N, roots_h, weights, args.cpu_seconds, threads)
+        if selfplay:
+            sample += " (searches only; the env step and bookkeeping are negligible next to them)"
         cpu = {"value": v, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample}
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
@@ -318,15 +383,19 @@ def main():
             "metric": "MCTS simulations/sec (batched trees)", "value": total_sims / (ms_max * 1e-3), "unit": "sims/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 tree statistics + env dynamics / f32 network", "data": "synthetic",
-            "config": {"workload": args.workload, "env": "Pendulum-v0" if variant == "continuous" else "CartPole-v0",
+            "dtype": "f64 tree statistics + env dynamics / " + ("f32 network with exact int8-sliced tensor-core products" if args.eval == "q8" else "f32 network"),
+            "data": "synthetic",
+            "config": {"workload": args.workload, "eval": args.eval, "env": "Pendulum-v0" if variant == "continuous" else "CartPole-v0",
                        "trees_per_gpu": B, "global_trees": B * world, "n_rollouts": N, "parallelism": f"tree-sharded x{world}, no data-path collective",
                        "weights": "default init, torch.manual_seed(34)", "roots": "numpy default_rng(34)",
                        "l2": "node tables per GPU (%.0f MB) exceed the 126 MB L2; no explicit flush" % (eng.rows * B * (32 + 16 + 32) / 1e6)
                        if variant == "continuous" else "tables are L2-resident at this size (SURVEY 8d config 3); no explicit flush"},
             "e2e": {"value": total_sims / (e2e_ms_max * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_max / args.steps, "api": "azg_search_host via SearchEngine.search_host (wall clock between syncs)"},
+                    "ms_per_step": e2e_ms_max / args.steps, "api": api},
             "gpu_launches": launches_per_step * args.steps,
+            **({"selfplay": {"max_episode_length": 200, "weight_broadcast_every_steps": SELFPLAY_BROADCAST_EVERY,
+                             "collectives_per_step": "all_gather of 5 replay-row tensors (C2); broadcast of the flat weights every k steps (C1)",
+                             "backend": "nccl" if world > 1 else "none (1 GPU)"}} if selfplay else {}),
             "clocks": clk,
             "roofline": dominant,
             "roofline_all": {"evaluation": roof_eval, "tree_step": roof_tree},
