@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
     extern __shared__ __align__(1024) uint8_t qsm_raw[];
     __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2];
     __shared__ uint32_t tmem_base_s;
-    uint8_t* qsm = reinterpret_cast<uint8_t*>(((uintptr_t)qsm_raw + 1023) & ~(uintptr_t)1023);
+    // round up to 1024 B with an OFFSET on the shared pointer: a round trip through uintptr_t loses the address space and every
+    // access below becomes a generic LD/ST (long-scoreboard latency) instead of LDS/STS
+    uint8_t* qsm = qsm_raw + ((1024u - (smem_u32(qsm_raw) & 1023u)) & 1023u);
     int8_t* sB = reinterpret_cast<int8_t*>(qsm);                     // [NL][3][8][128][16], rows permuted
     int8_t* sA = sB + (size_t)NL * 3 * QMLP_PLANE;                   // [2][3][8][128][16]
     float* fl = reinterpret_cast<float*>(sA + 2 * 3 * QMLP_PLANE);   // W0t[S][H], b0[H], NL x (cw, bias)[H], Wh[H][PO_PAD], bh[PO_PAD]
