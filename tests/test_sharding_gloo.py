@@ -52,3 +52,39 @@ def test_two_rank_sharded_search_equals_single_process(tmp_path):
     ref = azo.search(cfg, g["weights"], G.pendulum_roots(total, seed=11), tree_id0=0, dump=False)
     for k in KEYS:
         assert np.array_equal(got[k], ref[k]), k
+
+
+def _selfplay_worker(rank, world, port, total, steps, out_path):
+    """Self-play sharded over two ranks: each rank advances its environments (global ids keep the streams), the replay rows
+    of every step are all-gathered (C2) into a DeviceReplayBuffer on CPU tensors."""
+    from oracle import selfplay as osp
+    from alphazero_gym_b200.selfplay import DeviceReplayBuffer, ROW_KEYS, initial_states
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg, g = G.load("pendulum_n25_k2")
+        cfg.use_eval_tape = 0
+        lo, hi = shard_range(total, rank, world)
+        states0 = initial_states(cfg.variant, hi - lo, seed=3, tree_id0=lo, total=total)
+        recs = osp.run(cfg, g["weights"], states0, steps, 2, seed=cfg.seed, tree_id0=lo, n_threads=1)
+        rb = DeviceReplayBuffer(max_size=total * steps, batch_size=8, obs_dim=3, cmax=cfg.cmax, device="cpu")
+        for r in recs:
+            rb.store(allgather_results(results_to_torch({k: r[k] for k in ROW_KEYS}), total))
+        if rank == 0:
+            np.savez(out_path, **{k: rb.data[k][: len(rb)].numpy() for k in ROW_KEYS})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_selfplay_replay_equals_single_process(tmp_path):
+    from oracle import selfplay as osp
+    from alphazero_gym_b200.selfplay import ROW_KEYS, initial_states
+    total, world, steps = 13, 2, 3
+    out = str(tmp_path / "replay.npz")
+    mp.spawn(_selfplay_worker, args=(world, _free_port(), total, steps, out), nprocs=world, join=True)
+    got = np.load(out)
+    cfg, g = G.load("pendulum_n25_k2")
+    cfg.use_eval_tape = 0
+    recs = osp.run(cfg, g["weights"], initial_states(cfg.variant, total, seed=3), steps, 2, seed=cfg.seed, n_threads=1)
+    for k in ROW_KEYS:
+        assert np.array_equal(got[k], np.concatenate([r[k] for r in recs], 0)), k
