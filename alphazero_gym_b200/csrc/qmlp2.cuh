@@ -10,8 +10,10 @@
 //   * each H x H layer is issued as two N = 64 halves into a 192-column accumulator window per tile (PA | PB | PC, 64
 //     columns each): the epilogue of half 0 overlaps the MMAs of half 1, and two tiles fit the 512 TMEM columns
 //     (2 x 192 + 2 x 64 columns of scratch for the head partial sums);
-//   * the only thread barriers left are 128-thread named barriers among the four warps that share a row group (row maximum,
-//     head partial sums); the tile's post-processing rotates over those four warps;
+//   * a third warpgroup post-processes finished tiles (sum of the head partial sums, softmax / exp of the policy head, scatter
+//     into the tree tables): on the epilogue warps that work made one warp of a row group late at every tile and the other
+//     three waited for it (12 % of the samples, profiles/r1e);
+//   * the only thread barrier left is a 128-thread named barrier among the four warps that share a row group (row maximum);
 //   * the tile is a RUN-TIME index everywhere (one copy of the epilogue code: the first version, specialised per tile and
 //     layer, was 210 KB of SASS and starved on instruction fetch): the 16 activations a thread produces in half 0 wait for
 //     half 1 in the tile's TMEM scratch columns, not in registers.
@@ -24,7 +26,7 @@
 #include "qmlp.cuh"
 
 #define Q2_EPI_THREADS 512
-#define Q2_THREADS 640                // 16 epilogue warps + the warpgroup of the MMA warp (registers are rebalanced with setmaxnreg)
+#define Q2_THREADS 768                // 16 epilogue warps + the MMA warpgroup + the post-processing warpgroup (registers rebalanced with setmaxnreg)
 #define Q2_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24))  // s8 x s8 -> s32, K-major, N = 64, M = 128
 #define Q2_ACC_COLS 192               // accumulator window of a tile: PA | PB | PC, 64 columns each
 #define Q2_SCRATCH_COL 384            // head partial sums of tile T: columns 384 + 64 T + 16 cq + c
@@ -90,7 +92,7 @@ struct Q2Ctx {
     const float* bh;     // [PO_PAD]
     float* pmax;         // [2][4][128]
     int8_t* sA;          // [2][3][QMLP_PLANE]
-    uint64_t *full, *ready, *freeb;
+    uint64_t *full, *ready, *freeb, *hfull;
     uint32_t tb;         // TMEM base
     int r, lg, cq;
 };
@@ -148,54 +150,61 @@ __device__ __forceinline__ float q2_layer0(const Q2Ctx& c, const MlpParams& p, i
     return q2_quantise_store(c, T, wact, a, a + 16, pm);
 }
 
-// heads: partial FMA chains over this thread's 32 activations -> TMEM scratch -> one thread per row sums them and post-processes
-__device__ __forceinline__ void q2_heads(const Q2Ctx& c, const MlpParams& p, int T, const float* a0, const float* a1, bool finisher,
-                                         bool need, int gr, int leafw, double lr, uint32_t& nev, int& ev_row) {
-    const uint32_t lane_base = c.tb + ((uint32_t)(c.lg * 32) << 16) + Q2_SCRATCH_COL + T * 64;
-#pragma unroll 1
-    for (int c4 = 0; c4 < p.PO_PAD / 4; ++c4) {
-        float2 lo = make_float2(0.0f, 0.0f), hi = make_float2(0.0f, 0.0f);
-        const float* wp = c.Wh + (c.cq * 32) * p.PO_PAD + c4 * 4;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wp + i * p.PO_PAD);
-            const float ai = i < 16 ? a0[i & 15] : a1[i & 15];
-            const float2 av = make_float2(ai, ai);
-            lo = __ffma2_rn(av, make_float2(w4.x, w4.y), lo);
-            hi = __ffma2_rn(av, make_float2(w4.z, w4.w), hi);
-        }
-        tmem_st4f(lane_base + c.cq * 16 + c4 * 4, lo.x, lo.y, hi.x, hi.y);
-    }
-    tmem_wait_st();
-    tc_fence_before();
-    group_sync(1 + c.lg, 128);
-    tc_fence_after();
-    if (finisher) {  // warp-uniform
-        float out[Q2_MAX_PO];
+// heads: partial FMA chains over this thread's 32 activations -> the tile's TMEM scratch -> "hfull" (the post-processing warps
+// sum the four partials of every output and finish the row)
+__device__ __forceinline__ void q2_heads(const Q2Ctx& c, const MlpParams& p, int T, bool wact, const float* a0, const float* a1) {
+    if (wact) {
+        const uint32_t lane_base = c.tb + ((uint32_t)(c.lg * 32) << 16) + Q2_SCRATCH_COL + T * 64;
 #pragma unroll 1
         for (int c4 = 0; c4 < p.PO_PAD / 4; ++c4) {
-            float q0[4], q1[4], q2[4], q3[4];
-            tmem_ld4f(lane_base + c4 * 4, q0);
-            tmem_ld4f(lane_base + 16 + c4 * 4, q1);
-            tmem_ld4f(lane_base + 32 + c4 * 4, q2);
-            tmem_ld4f(lane_base + 48 + c4 * 4, q3);
-            tmem_wait_ld();
+            float2 lo = make_float2(0.0f, 0.0f), hi = make_float2(0.0f, 0.0f);
+            const float* wp = c.Wh + (c.cq * 32) * p.PO_PAD + c4 * 4;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                out[c4 * 4 + i] = __fadd_rn(__fadd_rn(__fadd_rn(q0[i], q1[i]), __fadd_rn(q2[i], q3[i])), c.bh[c4 * 4 + i]);
+            for (int i = 0; i < 32; ++i) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wp + i * p.PO_PAD);
+                const float ai = i < 16 ? a0[i & 15] : a1[i & 15];
+                const float2 av = make_float2(ai, ai);
+                lo = __ffma2_rn(av, make_float2(w4.x, w4.y), lo);
+                hi = __ffma2_rn(av, make_float2(w4.z, w4.w), hi);
+            }
+            tmem_st4f(lane_base + c.cq * 16 + c4 * 4, lo.x, lo.y, hi.x, hi.y);
         }
-        if (need) {
-            mlp_finish_row(p, gr, leafw, lr, out[0], out + 1);
-            ++nev;
-            ev_row = gr;
-        }
+        tmem_wait_st();
+    }
+    tc_fence_before();
+    mbar_arrive(c.hfull + T);
+}
+
+// post-processing warp of row group lg: one thread per row of the tile in slot T
+__device__ __forceinline__ void q2_finish_tile(const MlpParams& p, uint32_t tb, const float* bh, int lg, int T, bool need, int gr, int leafw,
+                                               double lr, uint64_t* hfree, uint32_t& nev, int& ev_row) {
+    const uint32_t lane_base = tb + ((uint32_t)(lg * 32) << 16) + Q2_SCRATCH_COL + T * 64;
+    float out[Q2_MAX_PO];
+#pragma unroll 1
+    for (int c4 = 0; c4 < p.PO_PAD / 4; ++c4) {
+        float q0[4], q1[4], q2[4], q3[4];
+        tmem_ld4f(lane_base + c4 * 4, q0);
+        tmem_ld4f(lane_base + 16 + c4 * 4, q1);
+        tmem_ld4f(lane_base + 32 + c4 * 4, q2);
+        tmem_ld4f(lane_base + 48 + c4 * 4, q3);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            out[c4 * 4 + i] = __fadd_rn(__fadd_rn(__fadd_rn(q0[i], q1[i]), __fadd_rn(q2[i], q3[i])), bh[c4 * 4 + i]);
+    }
+    tc_fence_before();
+    mbar_arrive(hfree + T);  // the scratch columns may be reused (half-0 activations of the next tile in this slot)
+    if (need) {
+        mlp_finish_row(p, gr, leafw, lr, out[0], out + 1);
+        ++nev;
+        ev_row = gr;
     }
 }
 
 template <int S, int ACT, int NL>
 __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
     extern __shared__ __align__(1024) uint8_t qsm_raw[];
-    __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2];
+    __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2], hfull[2], hfree[2];
     __shared__ uint32_t tmem_base_s;
     // round up to 1024 B with an OFFSET on the shared pointer: a round trip through uintptr_t loses the address space and every
     // access below becomes a generic LD/ST (long-scoreboard latency) instead of LDS/STS
@@ -223,6 +232,8 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
             mbar_init(&full[T], 1);
             mbar_init(&ready[T], Q2_EPI_THREADS);
             mbar_init(&freeb[T], Q2_EPI_THREADS);
+            mbar_init(&hfull[T], Q2_EPI_THREADS);
+            mbar_init(&hfree[T], 128);
         }
     }
     if (warp == 0) {
@@ -241,7 +252,41 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
     }
     mbar_wait(&wbar, 0);
 
-    if (warp >= 16) {
+    if (warp >= 20) {
+        // ---- post-processing warpgroup: warp 20 + lg finishes the rows of row group lg, tile after tile
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int lg = warp & 3, r = lg * 32 + lane;
+        const float* bh = fl + S * 128 + 128 + NL * 2 * 128 + 128 * p.PO_PAD;
+        uint32_t hph = 0, nev = 0;
+        int ev_row = 0;
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
+            const int T = t & 1;
+            const int row0 = row_begin + t * th;
+            const int nv = max(0, min(th, row_end - row0));
+            const int gr = row0 + r;
+            bool need = r < nv;
+            int leafw = 0;
+            double lr = 0.0;
+            if (need && p.mode == 0) {  // loaded before the wait: the latency hides under the tile's evaluation
+                if (p.variant == 1) {
+                    const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
+                    const uint4 c0 = cp[0], c1 = cp[1];
+                    leafw = (int)c0.z;
+                    lr = __hiloint2double((int)c1.w, (int)c1.z);
+                } else {
+                    leafw = p.leaf[gr];
+                }
+                need = (leafw & LEAF_EVAL) != 0;
+            }
+            mbar_wait(&hfull[T], (hph >> T) & 1u);
+            hph ^= 1u << T;
+            tc_fence_after();
+            if (lg * 32 < nv) q2_finish_tile(p, tb, bh, lg, T, need, gr, leafw, lr, hfree, nev, ev_row);
+            else mbar_arrive(&hfree[T]);
+        }
+        if (nev && p.mode == 0) p.evals[ev_row] += nev;  // only the total over trees is reported (azg_get_counters)
+    } else if (warp >= 16) {
         // ---- MMA warpgroup: gives its registers to the epilogue warps; one thread issues, in the order the epilogue warps consume
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (warp == 16 && lane == 0) {
@@ -279,7 +324,7 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
         }
     } else {
         // ---- epilogue warps
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");  // 512 x 112 + 128 x 24 <= 640 x 96, the CTA's pool at launch
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 512 x 104 + 128 x 24 + 128 x 40 = 768 x 80, the CTA's pool at launch
         Q2Ctx c;
         c.W0 = fl;
         c.b0 = fl + S * 128;
@@ -288,45 +333,22 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
         c.bh = c.Wh + 128 * p.PO_PAD;
         c.pmax = pmax;
         c.sA = sA;
-        c.full = full; c.ready = ready; c.freeb = freeb;
+        c.full = full; c.ready = ready; c.freeb = freeb; c.hfull = hfull;
         c.tb = tb;
         c.lg = warp & 3; c.cq = warp >> 2;
         c.r = c.lg * 32 + lane;
         uint32_t fullph = 0;  // bit T: parity of the next wait on full[T]
-        uint32_t nev = 0;     // rows this thread post-processed; added to the per-tree evaluation counters once, at the end
-        int ev_row = 0;
+        uint32_t hfph = 0;    // bit T: parity of the next wait on hfree[T]
 #pragma unroll 1
         for (int t0 = 0; t0 < ntiles; t0 += 2) {
             const int nt = min(2, ntiles - t0);
-            // per-slot state (slot T holds tile t0 + T): scale of the layer input, and for the rows this thread post-processes
-            // the leaf word / reward (needed only when the tile is finished; loaded here so the latency is hidden)
-            float cx0 = 0.0f, cx1 = 0.0f;
-            int leafw0 = 0, leafw1 = 0;
-            double lr0 = 0.0, lr1 = 0.0;
-            bool need0 = false, need1 = false;
+            float cx0 = 0.0f, cx1 = 0.0f;  // per slot (slot T holds tile t0 + T): scale of the current layer's input
 #pragma unroll 1
             for (int T = 0; T < nt; ++T) {
                 const int row0 = row_begin + (t0 + T) * th;
                 const int nv = max(0, min(th, row_end - row0));
-                const bool wact = c.lg * 32 < nv, valid = c.r < nv;
-                const int gr = row0 + c.r;
-                bool need = valid && c.cq == ((t0 + T) & 3);
-                int leafw = 0;
-                double lr = 0.0;
-                if (need && p.mode == 0) {
-                    if (p.variant == 1) {
-                        const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
-                        const uint4 c0 = cp[0], c1 = cp[1];
-                        leafw = (int)c0.z;
-                        lr = __hiloint2double((int)c1.w, (int)c1.z);
-                    } else {
-                        leafw = p.leaf[gr];
-                    }
-                    need = (leafw & LEAF_EVAL) != 0;
-                }
-                const float cx = q2_layer0<S, ACT>(c, p, T, wact, gr, valid);
-                if (T == 0) { cx0 = cx; leafw0 = leafw; lr0 = lr; need0 = need; }
-                else { cx1 = cx; leafw1 = leafw; lr1 = lr; need1 = need; }
+                const float cx = q2_layer0<S, ACT>(c, p, T, c.lg * 32 < nv, row0 + c.r, c.r < nv);
+                if (T == 0) cx0 = cx; else cx1 = cx;
             }
 #pragma unroll 1
             for (int step = 0; step < NL * 2 * nt; ++step) {
@@ -370,6 +392,11 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
                     if (h == 0) mbar_arrive(freeb + T);
                 }
                 if (h == 0) {
+                    if (l == 0 && t0 > 0) {  // the slot's scratch still holds the head partial sums of its previous tile
+                        mbar_wait(hfree + T, (hfph >> T) & 1u);
+                        hfph ^= 1u << T;
+                        tc_fence_after();
+                    }
                     if (wact) {  // park the first 16 activations until half 1 is done (only this thread reads them back)
                         tmem_st16f(stash, v);
                         tmem_wait_st();
@@ -385,13 +412,12 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
                     if (l + 1 < NL) {
                         const float ncx = q2_quantise_store(c, T, wact, u, v, pm);
                         if (T) cx1 = ncx; else cx0 = ncx;
-                    } else if (wact) {
-                        q2_heads(c, p, T, u, v, c.cq == ((t0 + T) & 3), T ? need1 : need0, row0 + c.r, T ? leafw1 : leafw0, T ? lr1 : lr0, nev, ev_row);
+                    } else {
+                        q2_heads(c, p, T, wact, u, v);
                     }
                 }
             }
         }
-        if (nev && p.mode == 0) p.evals[ev_row] += nev;  // only the total over trees is reported (azg_get_counters)
     }
     tc_fence_before();
     __syncthreads();

@@ -23,6 +23,8 @@
 #include "common.cuh"
 #include "env.cuh"
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ CHot load_hot(const void* p) {
     CHot h;
     const uint4* s = reinterpret_cast<const uint4*>(p);
@@ -214,9 +216,27 @@ __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
     CRow* rows = p.crows + (size_t)t * p.R;
     CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
     uint8_t* path_ovf = p.path + (size_t)t * p.R;
+    // The kernel is a chain of dependent DRAM round trips per tree (profiles/r1d_lines_step.txt: 64 % of the stall samples are
+    // long-scoreboard).  Everything whose address is known early is requested early: the root edge table depends on t only,
+    // the per-tree counters are read here instead of read-modify-written at the end, the path rows are requested as soon as
+    // the control block arrives.
+    if (SELECT) {
+        prefetch_l2(et);
+        prefetch_l2(reinterpret_cast<const char*>(et) + 128);
+    }
+    uint32_t ctr_levels = 0, ctr_scanned = 0;
+    if (SELECT) { ctr_levels = p.ctr[t]; ctr_scanned = p.ctr[(size_t)p.B + t]; }
     CCtl c = load_ctl(p.ctl + t);
     uint32_t pathw[4];
     memcpy(pathw, c.path, 16);
+    if (BACKUP) {
+        const int d = c.depth < 16 ? c.depth : 16;
+        for (int i = 1; i < d; ++i) prefetch_l2(rows + list_byte(pathw, i));
+    }
+    if (SELECT && c.root_nk > 8) {
+        prefetch_l2(reinterpret_cast<const char*>(et) + 256);
+        if (c.root_nk > 12) prefetch_l2(reinterpret_cast<const char*>(et) + 384);
+    }
 
     if (BACKUP) {
         // backprop (mcts.py:241-267) along the recorded path.  leafR already holds r_leaf + gamma*V_leaf
@@ -268,6 +288,7 @@ __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
             cur_nn = sh.nn_flags & CROW_NMASK;
             cur_V = sh.V;
             if (sh.nn_flags & CROW_TERMINAL) { kind = KIND_TERMINAL; leaf_r = sh.r; (void)from_root; break; }
+            prefetch_l2(p.chead + ((size_t)t * p.R + cur) * p.HS);  // read if the tree widens at this node
             const CSec1 s1 = load_sec1(rows + cur);
             kw[0] = s1.kw[0]; kw[1] = s1.kw[1]; kw[2] = s1.kw[2]; kw[3] = s1.kw[3];
             nk = (int)(kw[3] >> 24);
@@ -333,8 +354,8 @@ __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
         c.draws = draws;
         c.pw = (uint16_t)pwc;
         c.depth = (uint8_t)depth;
-        p.ctr[t] += levels;
-        p.ctr[(size_t)p.B + t] += scanned;
+        p.ctr[t] = ctr_levels + levels;
+        p.ctr[(size_t)p.B + t] = ctr_scanned + scanned;
         memcpy(c.root_kids, rootk, 16);
     }
     memcpy(c.path, pathw, 16);
