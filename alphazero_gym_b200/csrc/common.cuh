@@ -16,6 +16,7 @@
 
 #define AZG_MAX_K 8
 #define AZG_PENDULUM_R_SCALE 16.2736044 /* mcts.py:20 */
+#define AZG_TAB 1024
 
 // ---- hot rows ----------------------------------------------------------------------------------
 struct __align__(16) DRow {  // NodeDiscrete + its ActionDiscrete[2]   (states.py:115-191, :292-362)
@@ -106,6 +107,8 @@ struct TreeParams {
     CHot* et;         // [B][16]  root edge table: hot sectors of the root's children, insertion order
     CCtl* ctl;        // [B]      control blocks
     const int32_t* pw_table;  // [max_rollouts + 2]  ceil(c_pw * (n+1)^kappa), built on the host
+    const double* rcp_tab;    // [AZG_TAB + 1]  1.0 / i  (host-built, correctly rounded), see div_small
+    const double* sqrt_tab;   // [AZG_TAB + 1]  sqrt(i)
     // per-tree scalars
     // per-tree scalars of the discrete tree (the continuous tree keeps them in CCtl)
     int32_t* n_rows;  // rows / nodes in use
@@ -122,6 +125,24 @@ struct TreeParams {
     const float* tapeP;
     const float* tapeA;
 };
+
+// ---- IEEE division by a small integer without the division routine ------------------------------------------------
+// Q = W / n and sqrt(N + 1) / (n + 1) sit on the select chain between two dependent loads, and DDIV / DSQRT are ~40-instruction
+// dependent sequences.  With y = RN(1 / b) from a table: q = RN(a y), r = a - q b (exact in one fma), RN(q + r y) is the
+// correctly rounded quotient a / b (Markstein's final division step; b is a small integer, so the one exceptional divisor
+// pattern, an all-ones significand, cannot occur; 4e8 random cases checked against a / b on the CPU).  Zero, subnormal-range
+// and non-finite numerators take the ordinary division.
+__device__ __forceinline__ double div_small(double a, int b, const double* __restrict__ rcp) {
+    const double fa = fabs(a);
+    if (b > AZG_TAB || !(fa > 1e-250 && fa < 1e250)) return a / (double)b;
+    const double y = __ldg(rcp + b);
+    const double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-q, (double)b, a);
+    return __fma_rn(r, y, q);
+}
+__device__ __forceinline__ double sqrt_small(int n, const double* __restrict__ tab) {
+    return n <= AZG_TAB ? __ldg(tab + n) : sqrt((double)n);
+}
 
 // ---- Philox4x32-10 (Salmon et al. SC'11); counter layout documented in DESIGN.md section 5 ---------
 struct u32x4 { uint32_t x, y, z, w; };

@@ -60,6 +60,7 @@ struct azg_engine {
     int32_t* err = nullptr;
     float* wpack = nullptr;
     uint64_t* d_seed = nullptr;  // Philox key read by the kernels (azg_set_seed)
+    double* dtab = nullptr;      // rcp_tab[AZG_TAB + 1], sqrt_tab[AZG_TAB + 1] (common.cuh div_small)
     // AZG_FLAG_EVAL_Q8: int8 digit planes + f32 side table of the tensor-core evaluation kernel (qmlp.cuh)
     int8_t* qdigits = nullptr;
     float* qfl = nullptr;
@@ -106,7 +107,7 @@ extern "C" void azg_destroy(azg_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     void* ptrs[] = {e->drows, e->dstate, e->crows, e->et, e->ctl, e->chead, e->pw_table, e->n_rows, e->draws,
-                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->qdigits, e->qfl, e->r_actions,
+                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->dtab, e->qdigits, e->qfl, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -215,6 +216,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(err, 1);
     ALLOC(wpack, (size_t)e->wcount);
     ALLOC(d_seed, 1);
+    ALLOC(dtab, 2 * (AZG_TAB + 1));
     if (e->q8) {
         ALLOC(qdigits, (size_t)(c.n_hidden - 1) * 3 * QMLP_PLANE);
         ALLOC(qfl, (size_t)e->qfl_count);
@@ -223,6 +225,15 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
 #undef ALLOC
     CK(cudaMemset(e->err, 0, sizeof(int32_t)));
     CK(cudaMemcpy(e->d_seed, &c.seed, sizeof(uint64_t), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> tab(2 * (AZG_TAB + 1), 0.0);
+        for (int i = 1; i <= AZG_TAB; ++i) {
+            volatile double di = (double)i;
+            tab[i] = 1.0 / di;                      // IEEE division: correctly rounded
+            tab[AZG_TAB + 1 + i] = std::sqrt(di);   // IEEE sqrt: correctly rounded
+        }
+        CK(cudaMemcpy(e->dtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemset(e->n_rows, 0, B * sizeof(int32_t)));
     CK(cudaMemset(e->ctr, 0, 4 * B * sizeof(uint32_t)));
     {
@@ -383,6 +394,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.drows = e->drows; p.dstate = e->dstate;
     p.crows = e->crows; p.et = e->et; p.ctl = e->ctl; p.chead = e->chead;
     p.pw_table = e->pw_table;
+    p.rcp_tab = e->dtab; p.sqrt_tab = e->dtab + AZG_TAB + 1;
     p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path;
     p.ctr = e->ctr; p.X = e->X; p.root_state = e->root_state; p.root_n_init = e->root_n_init; p.err = e->err;
     p.tapeV = e->tapeV; p.tapeP = e->tapeP; p.tapeA = e->tapeA;

@@ -23,8 +23,6 @@
 #include "common.cuh"
 #include "env.cuh"
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __device__ __forceinline__ CHot load_hot(const void* p) {
     CHot h;
     const uint4* s = reinterpret_cast<const uint4*>(p);
@@ -173,7 +171,7 @@ __global__ void k_root_insert_continuous(const TreeParams p) {
 template <typename HotOf>
 __device__ __forceinline__ int uct_select(const TreeParams& p, int64_t tree, int nk, uint32_t cur_nn, float cur_V, int& draws, bool& nan,
                                           HotOf hot_of) {
-    const double sq = sqrt((double)(cur_nn + 1));
+    const double sq = sqrt_small((int)cur_nn + 1, p.sqrt_tab);
     double best = -CUDART_INF;
     uint32_t win = 0;
 #pragma unroll
@@ -187,8 +185,8 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, int64_t tree, int
                 const int j = w * 4 + i;
                 if (j < nk) {
                     const int n = c[i].n_e;
-                    const double Q = n > 0 ? c[i].W / (double)n : (double)cur_V;
-                    const double u = Q + p.c_uct * (sq / (double)(n + 1));  // mcts.py:731-732
+                    const double Q = n > 0 ? div_small(c[i].W, n, p.rcp_tab) : (double)cur_V;
+                    const double u = Q + p.c_uct * div_small(sq, n + 1, p.rcp_tab);  // mcts.py:731-732
                     nan |= (u != u);
                     if (u > best) { best = u; win = 1u << j; }
                     else if (u == best) win |= 1u << j;
@@ -216,27 +214,12 @@ __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
     CRow* rows = p.crows + (size_t)t * p.R;
     CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
     uint8_t* path_ovf = p.path + (size_t)t * p.R;
-    // The kernel is a chain of dependent DRAM round trips per tree (profiles/r1d_lines_step.txt: 64 % of the stall samples are
-    // long-scoreboard).  Everything whose address is known early is requested early: the root edge table depends on t only,
-    // the per-tree counters are read here instead of read-modify-written at the end, the path rows are requested as soon as
-    // the control block arrives.
-    if (SELECT) {
-        prefetch_l2(et);
-        prefetch_l2(reinterpret_cast<const char*>(et) + 128);
-    }
+    // per-tree counters: read here, written at the end (a read-modify-write at the end exposed the load latency)
     uint32_t ctr_levels = 0, ctr_scanned = 0;
     if (SELECT) { ctr_levels = p.ctr[t]; ctr_scanned = p.ctr[(size_t)p.B + t]; }
     CCtl c = load_ctl(p.ctl + t);
     uint32_t pathw[4];
     memcpy(pathw, c.path, 16);
-    if (BACKUP) {
-        const int d = c.depth < 16 ? c.depth : 16;
-        for (int i = 1; i < d; ++i) prefetch_l2(rows + list_byte(pathw, i));
-    }
-    if (SELECT && c.root_nk > 8) {
-        prefetch_l2(reinterpret_cast<const char*>(et) + 256);
-        if (c.root_nk > 12) prefetch_l2(reinterpret_cast<const char*>(et) + 384);
-    }
 
     if (BACKUP) {
         // backprop (mcts.py:241-267) along the recorded path.  leafR already holds r_leaf + gamma*V_leaf
@@ -288,7 +271,6 @@ __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
             cur_nn = sh.nn_flags & CROW_NMASK;
             cur_V = sh.V;
             if (sh.nn_flags & CROW_TERMINAL) { kind = KIND_TERMINAL; leaf_r = sh.r; (void)from_root; break; }
-            prefetch_l2(p.chead + ((size_t)t * p.R + cur) * p.HS);  // read if the tree widens at this node
             const CSec1 s1 = load_sec1(rows + cur);
             kw[0] = s1.kw[0]; kw[1] = s1.kw[1]; kw[2] = s1.kw[2]; kw[3] = s1.kw[3];
             nk = (int)(kw[3] >> 24);
