@@ -672,8 +672,13 @@ extern "C" int azg_search_host(azg_engine* e, int32_t B, const double* h_root_st
     int32_t* p_cnt = (int32_t*)hp; hp += (size_t)B * cm * sizeof(int32_t);
     int32_t* p_nc = (int32_t*)hp; hp += (size_t)B * sizeof(int32_t);
     int32_t* p_rn = (int32_t*)hp;
-    memcpy(p_root, h_root_state, (size_t)B * sd * sizeof(double));
-    CK(cudaMemcpyAsync(e->root_state, p_root, (size_t)B * sd * sizeof(double), cudaMemcpyHostToDevice, st));
+    {
+        cudaPointerAttributes at;
+        const bool root_pinned = cudaPointerGetAttributes(&at, h_root_state) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (!root_pinned) memcpy(p_root, h_root_state, (size_t)B * sd * sizeof(double));
+        CK(cudaMemcpyAsync(e->root_state, root_pinned ? h_root_state : p_root, (size_t)B * sd * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     const int32_t* d_rn = nullptr;
     if (h_root_n_init) {
         memcpy(p_rn, h_root_n_init, (size_t)B * sizeof(int32_t));
@@ -684,17 +689,28 @@ extern "C" int azg_search_host(azg_engine* e, int32_t B, const double* h_root_st
     if (rc) return rc;
     rc = azg_root_results(e, B, e->r_actions, e->r_counts, e->r_Q, e->r_Vt, e->r_nchild, st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(p_act, e->r_actions, (size_t)B * cm * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(p_cnt, e->r_counts, (size_t)B * cm * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(p_Q, e->r_Q, (size_t)B * cm * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(p_Vt, e->r_Vt, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(p_nc, e->r_nchild, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    // Output buffers that are page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) receive the results by DMA
+    // directly; pageable ones go through the engine's pinned staging buffer and one host memcpy each.
+    auto pinned = [](const void* h) {
+        cudaPointerAttributes at;
+        const bool ok = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return ok;
+    };
+    const bool direct = pinned(h_actions) && pinned(h_counts) && pinned(h_Q) && pinned(h_V_target) && pinned(h_n_children);
+    CK(cudaMemcpyAsync(direct ? h_actions : p_act, e->r_actions, (size_t)B * cm * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(direct ? h_counts : p_cnt, e->r_counts, (size_t)B * cm * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(direct ? h_Q : p_Q, e->r_Q, (size_t)B * cm * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(direct ? h_V_target : p_Vt, e->r_Vt, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(direct ? h_n_children : p_nc, e->r_nchild, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     rc = azg_status(e, st);  // synchronises
-    memcpy(h_actions, p_act, (size_t)B * cm * sizeof(float));
-    memcpy(h_counts, p_cnt, (size_t)B * cm * sizeof(int32_t));
-    memcpy(h_Q, p_Q, (size_t)B * cm * sizeof(double));
-    memcpy(h_V_target, p_Vt, (size_t)B * sizeof(double));
-    memcpy(h_n_children, p_nc, (size_t)B * sizeof(int32_t));
+    if (!direct) {
+        memcpy(h_actions, p_act, (size_t)B * cm * sizeof(float));
+        memcpy(h_counts, p_cnt, (size_t)B * cm * sizeof(int32_t));
+        memcpy(h_Q, p_Q, (size_t)B * cm * sizeof(double));
+        memcpy(h_V_target, p_Vt, (size_t)B * sizeof(double));
+        memcpy(h_n_children, p_nc, (size_t)B * sizeof(int32_t));
+    }
     return rc;
 }
 

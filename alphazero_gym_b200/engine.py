@@ -162,14 +162,27 @@ class SearchEngine:
             check(self._lib.azg_status(self._h, self._stream()))
 
     # ---- host-buffer path (what MCTS*.search + return_results cost end to end) ---------------------
+    def host_buffers(self, B: int) -> Dict[str, np.ndarray]:
+        """Page-locked result buffers for search_host(out=...): the engine DMAs into them directly (no staging copy)."""
+        t = dict(actions=torch.empty((B, self.cmax), dtype=torch.float32).pin_memory(),
+                 counts=torch.empty((B, self.cmax), dtype=torch.int32).pin_memory(),
+                 Q=torch.empty((B, self.cmax), dtype=torch.float64).pin_memory(),
+                 V_target=torch.empty(B, dtype=torch.float64).pin_memory(),
+                 n_children=torch.empty(B, dtype=torch.int32).pin_memory())
+        self._keep[("host_buffers", B)] = t
+        return {k: v.numpy() for k, v in t.items()}
+
     def search_host(self, root_state: np.ndarray, n_rollouts: int, root_n_init: Optional[np.ndarray] = None,
-                    tree_id0: int = 0) -> Dict[str, np.ndarray]:
+                    tree_id0: int = 0, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """Host buffers in, host buffers out (azg_search_host).  `out` (e.g. from host_buffers) is reused if given."""
         rs = np.ascontiguousarray(root_state, np.float64).reshape(-1, self.state_cols)
         B = rs.shape[0]
         rn = None if root_n_init is None else np.ascontiguousarray(root_n_init, np.int32)
-        out = dict(actions=np.empty((B, self.cmax), np.float32), counts=np.empty((B, self.cmax), np.int32),
-                   Q=np.empty((B, self.cmax), np.float64), V_target=np.empty(B, np.float64),
-                   n_children=np.empty(B, np.int32))
+        if out is None:
+            out = dict(actions=np.empty((B, self.cmax), np.float32), counts=np.empty((B, self.cmax), np.int32),
+                       Q=np.empty((B, self.cmax), np.float64), V_target=np.empty(B, np.float64),
+                       n_children=np.empty(B, np.int32))
+        assert out["actions"].shape == (B, self.cmax) and out["Q"].dtype == np.float64
         check(self._lib.azg_search_host(self._h, B, _ptr(rs), _ptr(rn), n_rollouts, tree_id0, _ptr(out["actions"]),
                                         _ptr(out["counts"]), _ptr(out["Q"]), _ptr(out["V_target"]), _ptr(out["n_children"])))
         self.last_B = B

@@ -244,7 +244,7 @@ def main():
     roots_d = torch.from_numpy(roots_h).cuda()
 
     selfplay = args.workload.startswith("selfplay")
-    api = "azg_search_host via SearchEngine.search_host (wall clock between syncs)"
+    api = "azg_search_host via SearchEngine.search_host, page-locked host buffers (wall clock between syncs)"
     if selfplay:
         # ---- self-play loop (BASELINE config 5): search -> final action -> real env step, replay rows all-gathered every
         # step (C2), weights re-broadcast from rank 0 and re-loaded every SELFPLAY_BROADCAST_EVERY steps (C1)
@@ -281,8 +281,11 @@ def main():
             eng.search(roots_d, N, tree_id0=tree_id0)
             return eng.root_results()
 
+        host_out = eng.host_buffers(B)  # page-locked, as the contract asks: results arrive by DMA, no staging copy
+        roots_pinned = torch.from_numpy(roots_h).pin_memory().numpy()
+
         def host_step(i):
-            return eng.search_host(roots_h, N, tree_id0=tree_id0)
+            return eng.search_host(roots_pinned, N, tree_id0=tree_id0, out=host_out)
 
         h2d = roots_h.nbytes
         extra_launches = 1  # the root-results kernel

@@ -189,3 +189,24 @@ def test_errors():
             eng.search(torch.zeros((5, 2), dtype=torch.float64, device="cuda"), 25)
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_host_entry_point_with_page_locked_buffers():
+    """azg_search_host DMAs straight into page-locked caller buffers; same bits as the staged path for pageable ones."""
+    import enginelib as E
+    import torch
+    cfg, g = G.load("pendulum_n25_k2")
+    cfg.math_mode, cfg.use_eval_tape = azo.MATH_DET, 0
+    roots = G.pendulum_roots(300, seed=3)
+    eng = E.SearchEngine(E.engine_config(cfg, 300))
+    try:
+        eng.set_weights(g["weights"])
+        a = eng.search_host(roots, cfg.n_rollouts, tree_id0=5)
+        out = eng.host_buffers(300)
+        b = eng.search_host(torch.from_numpy(roots).pin_memory().numpy(), cfg.n_rollouts, tree_id0=5, out=out)
+        assert b is out
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    finally:
+        eng.close()
