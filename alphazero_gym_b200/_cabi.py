@@ -17,6 +17,7 @@ ACT_RELU, ACT_ELU = 0, 1
 VT = {"off_policy": 0, "on_policy": 1, "greedy": 2}
 FLAG_NO_GRAPH = 1
 FLAG_EVAL_Q8 = 2
+FLAG_FUSED = 4
 
 EXPORTS = [
     "azg_create", "azg_destroy", "azg_last_error", "azg_version", "azg_num_weights", "azg_set_weights",

@@ -67,6 +67,7 @@ struct azg_engine {
     int qfl_count = 0;
     size_t qmlp_smem = 0;
     bool q8 = false;
+    bool fused = false;  // AZG_FLAG_FUSED: the whole continuous search in one persistent kernel (qmlp2.cuh)
     // results staging (device) + pinned host staging for the *_host entry point
     float* r_actions = nullptr;
     int32_t* r_counts = nullptr;
@@ -169,6 +170,11 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
             delete e;
             return fail(AZG_EINVAL, "AZG_FLAG_EVAL_Q8 needs hidden = 128, n_hidden in {2, 3}, at most 15 head outputs and an sm_100 device (tcgen05)");
         }
+    }
+    e->fused = (c.flags & AZG_FLAG_FUSED) != 0;
+    if (e->fused && !(e->q8 && c.variant == AZG_CONTINUOUS && c.state_dim == 3)) {
+        delete e;
+        return fail(AZG_EINVAL, "AZG_FLAG_FUSED needs the continuous variant with AZG_FLAG_EVAL_Q8");
     }
     const size_t B = c.max_trees, R = e->R;
     std::vector<int32_t> pwt;
@@ -427,10 +433,40 @@ static cudaError_t launch_mlp_t(const azg_engine* e, const MlpParams& m, cudaStr
 
 template <int S, int ACT, int NL>
 static cudaError_t launch_qmlp_t(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr) {
-    if (set_attr) return cudaFuncSetAttribute(k_qmlp2<S, ACT, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
+    if (set_attr) {
+        cudaError_t ce = cudaFuncSetAttribute(k_qmlp2<S, ACT, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
+        if (ce != cudaSuccess) return ce;
+        return cudaFuncSetAttribute(k_qmlp2<S, ACT, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
+    }
     const int grid = std::max(1, std::min((m.n + 127) / 128, e->sm_count));
-    k_qmlp2<S, ACT, NL><<<grid, Q2_THREADS, e->qmlp_smem, st>>>(m);
+    TreeParams none;
+    memset(&none, 0, sizeof none);
+    k_qmlp2<S, ACT, NL, false><<<grid, Q2_THREADS, e->qmlp_smem, st>>>(m, none, 0, 0, 0);
     return cudaGetLastError();
+}
+
+// whole-search kernel (AZG_FLAG_FUSED): one persistent launch per chunk of at most sm_count x Q2_MAX_TILES x 128 trees
+template <int S, int ACT, int NL>
+static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const TreeParams& p, int N, cudaStream_t st, int* launches) {
+    const int chunk = e->sm_count * Q2_MAX_TILES * 128;
+    for (int lo = 0; lo < p.B; lo += chunk) {
+        const int hi = std::min(p.B, lo + chunk);
+        const int grid = std::max(1, std::min((hi - lo + 127) / 128, e->sm_count));
+        k_qmlp2<S, ACT, NL, true><<<grid, Q2_FUSED_THREADS, e->qmlp_smem, st>>>(m, p, N, lo, hi);
+        ++*launches;
+        cudaError_t ce = cudaGetLastError();
+        if (ce != cudaSuccess) return ce;
+    }
+    return cudaSuccess;
+}
+
+static cudaError_t launch_fused(const azg_engine* e, const MlpParams& m, const TreeParams& p, int N, cudaStream_t st, int* launches) {
+    const int S = e->cfg.state_dim, A = e->cfg.activation, NL = e->cfg.n_hidden - 1;
+#define FUSED_CASE(s, a, nl) \
+    if (S == s && A == a && NL == nl) return launch_fused_t<s, a, nl>(e, m, p, N, st, launches);
+    FUSED_CASE(3, 0, 1) FUSED_CASE(3, 1, 1) FUSED_CASE(3, 0, 2) FUSED_CASE(3, 1, 2)
+#undef FUSED_CASE
+    return cudaErrorInvalidValue;
 }
 
 static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStream_t st, bool set_attr) {
@@ -504,6 +540,11 @@ static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStr
         }
         LK(0, (k_step_discrete<true, false><<<tg, tb, 0, st>>>(p)));
     } else {
+        if (e->fused && !tape && !prof) {  // the whole search in one persistent kernel per chunk of trees (qmlp2.cuh, FUSED)
+            ce = launch_fused(e, m, p, N, st, &launches);
+            *cerr = ce;
+            return launches;
+        }
         LK(2, (k_init_continuous<<<tg, tb, 0, st>>>(p)));
         if (!tape) LK(1, ce = launch_mlp(e, m, st, false));
         LK(2, (k_root_insert_continuous<<<tg, tb, 0, st>>>(p)));
@@ -540,7 +581,7 @@ static int run_search(azg_engine* e, int B, const double* d_root_state, const in
         }
     }
     cudaError_t ce = cudaSuccess;
-    if (e->cfg.flags & AZG_FLAG_NO_GRAPH) {
+    if ((e->cfg.flags & AZG_FLAG_NO_GRAPH) || (e->fused && !e->tapeV)) {  // the fused search is one launch per chunk: nothing to capture
         e->launches = enqueue_search(e, B, N, tree_id0, st, &ce);
         if (ce != cudaSuccess) return fail(AZG_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(ce));
     } else {

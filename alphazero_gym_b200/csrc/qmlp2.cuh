@@ -24,9 +24,12 @@
 // (k/16 = 2*cq + h) of the K-major A operand.
 #pragma once
 #include "qmlp.cuh"
+#include "tree_continuous.cuh"
 
 #define Q2_EPI_THREADS 512
 #define Q2_THREADS 768                // 16 epilogue warps + the MMA warpgroup + the post-processing warpgroup (registers rebalanced with setmaxnreg)
+#define Q2_FUSED_THREADS 896          // whole-search kernel: 16 epilogue warps + the MMA warpgroup + one tree warpgroup per tile slot
+#define Q2_MAX_TILES 16               // whole-search kernel: tiles per CTA and launch (engine.cu cuts larger batches into chunks)
 #define Q2_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24))  // s8 x s8 -> s32, K-major, N = 64, M = 128
 #define Q2_ACC_COLS 192               // accumulator window of a tile: PA | PB | PC, 64 columns each
 #define Q2_SCRATCH_COL 384            // head partial sums of tile T: columns 384 + 64 T + 16 cq + c
@@ -201,10 +204,24 @@ __device__ __forceinline__ void q2_finish_tile(const MlpParams& p, uint32_t tb, 
     }
 }
 
-template <int S, int ACT, int NL>
-__global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
+// FUSED = false: one leaf evaluation of p.n rows (one launch per simulation, engine.cu enqueue_search).
+// FUSED = true: the WHOLE SEARCH of the continuous tree for the trees [chunk_begin, chunk_end) in one persistent launch.
+//   Trees never interact, so nothing needs a grid-wide barrier between simulations: a CTA owns its trees for the whole search
+//   and runs n_sims + 1 evaluations of each of its tiles back to back.  The post-processing warpgroup becomes one TREE
+//   warpgroup per tile slot: thread r finishes row r of the tile (head sums, policy post-processing, scatter) and goes straight
+//   on to that tree's backup + select + expansion for the next simulation (c_step, tree_continuous.cuh: the body of
+//   k_step_continuous), writes the next network input and signals xready[tile].  While the trees of one tile pair walk their
+//   dependent loads (HBM/L2 latency bound, ~20 % of the issue slots of an SM), the epilogue warps evaluate the other pair, so the
+//   tree step costs no time of its own, the evaluation pipeline never drains between simulations, and the weights are staged once
+//   per search instead of once per simulation.  Every table of a tree is read and written by ONE thread for the whole search;
+//   the only cross-thread traffic is X (tree thread -> epilogue warps, release/acquire through xready) and the head partial sums
+//   (epilogue -> tree thread, through TMEM and hfull).
+template <int S, int ACT, int NL, bool FUSED>
+__global__ void __launch_bounds__(FUSED ? Q2_FUSED_THREADS : Q2_THREADS, 1)
+k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chunk_begin, const int chunk_end) {
     extern __shared__ __align__(1024) uint8_t qsm_raw[];
     __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2], hfull[2], hfree[2];
+    __shared__ __align__(8) uint64_t xready[FUSED ? Q2_MAX_TILES : 1];
     __shared__ uint32_t tmem_base_s;
     // round up to 1024 B with an OFFSET on the shared pointer: a round trip through uintptr_t loses the address space and every
     // access below becomes a generic LD/ST (long-scoreboard latency) instead of LDS/STS
@@ -217,9 +234,11 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // this CTA's contiguous row range, cut into an even number of equal tiles of at most 128 rows
-    const int per = (p.n + gridDim.x - 1) / gridDim.x;
-    const int row_begin = blockIdx.x * per;
-    const int row_end = min(row_begin + per, p.n);
+    const int first = FUSED ? chunk_begin : 0, last = FUSED ? chunk_end : p.n;
+    const int per = (last - first + gridDim.x - 1) / gridDim.x;
+    const int row_begin = first + blockIdx.x * per;
+    const int row_end = min(row_begin + per, last);
+    const int n_evals = FUSED ? n_sims + 1 : 1;  // evaluations per tile: the root + one per simulation
     if (row_begin >= row_end) return;
     const int nrows = row_end - row_begin;
     int ntiles = (nrows + 127) / 128;
@@ -235,6 +254,8 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
             mbar_init(&hfull[T], Q2_EPI_THREADS);
             mbar_init(&hfree[T], 128);
         }
+        if (FUSED)
+            for (int t = 0; t < Q2_MAX_TILES; ++t) mbar_init(&xready[t], 128);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
@@ -252,7 +273,52 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
     }
     mbar_wait(&wbar, 0);
 
-    if (warp >= 20) {
+    if (FUSED && warp >= 20) {
+        // ---- tree warpgroup of tile slot w: finishes the evaluated rows of its tiles and advances their trees
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        const int w = (warp - 20) >> 2, lg = warp & 3, r = lg * 32 + lane;
+        const float* bh = fl + S * 128 + 128 + NL * 2 * 128 + 128 * p.PO_PAD;
+        uint32_t hph = 0, nev = 0;
+        int ev_row = 0;
+#pragma unroll 1
+        for (int t = w; t < ntiles; t += 2) {  // MCTSContinuous.initialize_search for every tree of the tile
+            const int row0 = row_begin + t * th;
+            const int nv = max(0, min(th, row_end - row0));
+            if (r < nv) c_init(tp, row0 + r);
+            mbar_arrive(&xready[t]);
+        }
+#pragma unroll 1
+        for (int s = 0; s < n_evals; ++s) {
+#pragma unroll 1
+            for (int t = w; t < ntiles; t += 2) {
+                const int row0 = row_begin + t * th;
+                const int nv = max(0, min(th, row_end - row0));
+                const int gr = row0 + r;
+                const bool valid = r < nv;
+                bool need = valid;
+                int leafw = 0;
+                double lr = 0.0;
+                if (valid) {
+                    const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
+                    const uint4 c0 = cp[0], c1 = cp[1];
+                    leafw = (int)c0.z;
+                    lr = __hiloint2double((int)c1.w, (int)c1.z);
+                    need = (leafw & LEAF_EVAL) != 0;
+                }
+                mbar_wait(&hfull[w], hph);
+                hph ^= 1u;
+                tc_fence_after();
+                if (lg * 32 < nv) q2_finish_tile(p, tb, bh, lg, w, need, gr, leafw, lr, hfree, nev, ev_row);
+                else mbar_arrive(&hfree[w]);
+                if (valid) {
+                    if (s == 0) c_root_insert(tp, gr);         // the add_pw_action(root) before the loop (mcts.py:673)
+                    c_step(tp, gr, s > 0, s + 1 < n_evals);    // backup of simulation s, descent + expansion of simulation s + 1
+                }
+                if (s + 1 < n_evals) mbar_arrive(&xready[t]);  // releases X[gr] to the epilogue warps
+            }
+        }
+        if (nev) p.evals[ev_row] += nev;
+    } else if (warp >= 20) {
         // ---- post-processing warpgroup: warp 20 + lg finishes the rows of row group lg, tile after tile
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         const int lg = warp & 3, r = lg * 32 + lane;
@@ -291,6 +357,8 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         if (warp == 16 && lane == 0) {
             uint32_t rph = 0, fph = 0;  // bit T: parity of the next wait on ready[T] / freeb[T]
+#pragma unroll 1
+            for (int s = 0; s < n_evals; ++s)
             for (int t0 = 0; t0 < ntiles; t0 += 2) {
                 const int nt = min(2, ntiles - t0);
 #pragma unroll 1
@@ -324,7 +392,8 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
         }
     } else {
         // ---- epilogue warps
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 512 x 104 + 128 x 24 + 128 x 40 = 768 x 80, the CTA's pool at launch
+        if (FUSED) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");  // 512 x 96 + 128 x 24 + 256 x 48 = 896 x 72, the CTA's pool at launch
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");       // 512 x 104 + 128 x 24 + 128 x 40 = 768 x 80
         Q2Ctx c;
         c.W0 = fl;
         c.b0 = fl + S * 128;
@@ -340,6 +409,8 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
         uint32_t fullph = 0;  // bit T: parity of the next wait on full[T]
         uint32_t hfph = 0;    // bit T: parity of the next wait on hfree[T]
 #pragma unroll 1
+        for (int s = 0; s < n_evals; ++s)
+#pragma unroll 1
         for (int t0 = 0; t0 < ntiles; t0 += 2) {
             const int nt = min(2, ntiles - t0);
             float cx0 = 0.0f, cx1 = 0.0f;  // per slot (slot T holds tile t0 + T): scale of the current layer's input
@@ -347,6 +418,7 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
             for (int T = 0; T < nt; ++T) {
                 const int row0 = row_begin + (t0 + T) * th;
                 const int nv = max(0, min(th, row_end - row0));
+                if (FUSED) mbar_wait(&xready[t0 + T], (uint32_t)s & 1u);  // the tile's trees have written their next network inputs
                 const float cx = q2_layer0<S, ACT>(c, p, T, c.lg * 32 < nv, row0 + c.r, c.r < nv);
                 if (T == 0) cx0 = cx; else cx1 = cx;
             }
@@ -392,7 +464,7 @@ __global__ void __launch_bounds__(Q2_THREADS, 1) k_qmlp2(const MlpParams p) {
                     if (h == 0) mbar_arrive(freeb + T);
                 }
                 if (h == 0) {
-                    if (l == 0 && t0 > 0) {  // the slot's scratch still holds the head partial sums of its previous tile
+                    if (l == 0 && (t0 > 0 || s > 0)) {  // the slot's scratch still holds the head partial sums of its previous tile
                         mbar_wait(hfree + T, (hfph >> T) & 1u);
                         hfph ^= 1u << T;
                         tc_fence_after();

@@ -126,9 +126,7 @@ __device__ __forceinline__ CHot fresh_hot(double r, float V, float action, uint3
 }
 
 // MCTSContinuous.initialize_search (mcts.py:589-600): new root row, network input = obs(root)
-__global__ void k_init_continuous(const TreeParams p) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.B) return;
+__device__ __forceinline__ void c_init(const TreeParams& p, int t) {
     const double th = p.root_state[(size_t)t * 2], thdot = p.root_state[(size_t)t * 2 + 1];
     CRow* root = p.crows + (size_t)t * p.R;
     store_hot(root, fresh_hot(0.0, p.use_tape ? p.tapeV[(size_t)t * p.R] : 0.0f, 0.0f, CROW_EXPANDED));
@@ -141,11 +139,13 @@ __global__ void k_init_continuous(const TreeParams p) {
     store_ctl(p.ctl + t, c);
     for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
 }
+__global__ void k_init_continuous(const TreeParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.B) c_init(p, t);
+}
 
 // the add_pw_action(root) that precedes the rollout loop (mcts.py:673); runs after the root evaluation
-__global__ void k_root_insert_continuous(const TreeParams p) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.B) return;
+__device__ __forceinline__ void c_root_insert(const TreeParams& p, int t) {
     CRow* rows = p.crows + (size_t)t * p.R;
     CCtl c = load_ctl(p.ctl + t);
     const float a = new_action(p, t, 0, 1, 0);
@@ -159,6 +159,10 @@ __global__ void k_root_insert_continuous(const TreeParams p) {
     c.root_V = rows[0].V;  // written by the root evaluation
     c.root_nn = 0;
     store_ctl(p.ctl + t, c);
+}
+__global__ void k_root_insert_continuous(const TreeParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.B) c_root_insert(p, t);
 }
 
 #define KIND_INSERT 0    // progressive widening: create a new edge below `cur`, then its node
@@ -207,10 +211,9 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, int64_t tree, int
     return nw > 0 ? (int)__fns(win, 0, pick + 1) : 0;
 }
 
-template <bool BACKUP, bool SELECT>
-__global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.B) return;
+// one simulation step of tree t: backup of the previous simulation (BACKUP), then descent + expansion of the next (SELECT).
+// Shared by k_step_continuous (one launch per simulation) and the whole-search kernel k_search_fused (fused.cuh).
+__device__ __forceinline__ void c_step(const TreeParams& p, int t, const bool BACKUP, const bool SELECT) {
     CRow* rows = p.crows + (size_t)t * p.R;
     CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
     uint8_t* path_ovf = p.path + (size_t)t * p.R;
@@ -342,6 +345,11 @@ __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
     }
     memcpy(c.path, pathw, 16);
     store_ctl(p.ctl + t, c);
+}
+template <bool BACKUP, bool SELECT>
+__global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < p.B) c_step(p, t, BACKUP, SELECT);
 }
 
 // numpy pairwise summation for n <= 128 (np.sum in get_on_policy_value_target, mcts.py:111)

@@ -43,13 +43,19 @@ class EngineConfig:
     seed: int = 34
     use_graph: bool = True
     eval_q8: bool = False  # AZG_FLAG_EVAL_Q8: hidden x hidden layers on tcgen05 as exact int8-sliced products (include/azg.h)
+    fused: Optional[bool] = None  # AZG_FLAG_FUSED: whole search in one persistent kernel; None = on where supported (continuous + eval_q8)
 
     def c(self) -> AzgConfig:
         return AzgConfig(self.variant, self.max_rollouts, self.max_trees, self.num_actions, self.num_components,
                          self.state_dim, self.hidden, self.n_hidden, self.activation, VT[self.V_target_policy],
                          self.puct_f32, self.device, self.c_uct, float(self.gamma), self.epsilon, self.c_pw, self.kappa,
                          self.action_bound, self.log_std_min, self.log_std_max,
-                         (0 if self.use_graph else _cabi.FLAG_NO_GRAPH) | (_cabi.FLAG_EVAL_Q8 if self.eval_q8 else 0), self.seed)
+                         (0 if self.use_graph else _cabi.FLAG_NO_GRAPH) | (_cabi.FLAG_EVAL_Q8 if self.eval_q8 else 0)
+                         | (_cabi.FLAG_FUSED if self.is_fused() else 0), self.seed)
+
+    def is_fused(self) -> bool:
+        supported = bool(self.eval_q8) and self.variant == CONTINUOUS
+        return supported if self.fused is None else bool(self.fused)
 
 
 def flatten_state_dict(sd) -> np.ndarray:

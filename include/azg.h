@@ -67,6 +67,12 @@ typedef struct azg_config {
                                 Deterministic and bit-reproducible by the CPU oracle (AZO_EVAL_Q8); V error vs an f64
                                 evaluation is ~2x that of the FP32 path, well inside the 1e-5 parity tolerance. */
 
+#define AZG_FLAG_FUSED 4u    /* continuous variant with AZG_FLAG_EVAL_Q8: run the whole search (root evaluation, every simulation's
+                                backup + select + expansion + leaf evaluation) in ONE persistent kernel per chunk of trees; a CTA
+                                owns its trees for the whole search and overlaps the tree walk of one tile pair with the
+                                evaluation of the other.  Same arithmetic, same results bit for bit as the per-simulation
+                                launches. */
+
 typedef struct azg_engine azg_engine;
 
 int azg_create(const azg_config* cfg, azg_engine** out);

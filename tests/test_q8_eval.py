@@ -115,15 +115,25 @@ def test_q8_kernel_equals_oracle_bit_exact(name, n):
     assert np.array_equal(head[:2000], ho)
 
 
+def _fused_kw(cfg, fused):
+    """AZG_FLAG_FUSED (whole search in one persistent kernel) exists for the continuous variant only."""
+    if cfg.variant == azo.DISCRETE:
+        if fused:
+            pytest.skip("the whole-search kernel serves the continuous variant")
+        return {}
+    return {"fused": fused}
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("name", CASES)
-def test_q8_engine_equals_oracle_bit_exact(name):
+def test_q8_engine_equals_oracle_bit_exact(name, fused):
     import enginelib as E
     cfg, g = G.load(name)
     cfg.math_mode, cfg.use_eval_tape = azo.MATH_DET, 0
     _q8(cfg)
     ref = azo.search(cfg, g["weights"], g["root_state"], g.get("root_n_init"))
-    out = _fit(E, E.run_engine(cfg, g["weights"], g["root_state"], g.get("root_n_init")), ref)
+    out = _fit(E, E.run_engine(cfg, g["weights"], g["root_state"], g.get("root_n_init"), **_fused_kw(cfg, fused)), ref)
     assert_tree_equal(out, ref, cfg.variant == azo.DISCRETE, exact_fp=True)
     assert np.array_equal(out["counters"][:7], ref["counters"][:7])
 
@@ -139,8 +149,10 @@ def test_q8_engine_vs_reference_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant,B,N", [(azo.DISCRETE, 1024, 50), (azo.CONTINUOUS, 1024, 100), (azo.CONTINUOUS, 19000, 25)])
-def test_q8_random_batches_equal_oracle(variant, B, N):
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("variant,B,N", [(azo.DISCRETE, 1024, 50), (azo.CONTINUOUS, 1024, 100), (azo.CONTINUOUS, 19000, 25),
+                                         (azo.CONTINUOUS, 65536 + 77, 40)])
+def test_q8_random_batches_equal_oracle(variant, B, N, fused):
     import enginelib as E
     if variant == azo.DISCRETE:
         cfg, roots = azo.discrete_config(n_rollouts=N, epsilon=0.1), G.cartpole_roots(B, seed=7)
@@ -149,8 +161,28 @@ def test_q8_random_batches_equal_oracle(variant, B, N):
     _q8(cfg)
     rng = np.random.default_rng(5)
     w = (rng.standard_normal(cfg.num_weights) * 0.08).astype(np.float32)
+    kw = _fused_kw(cfg, fused)
     ref = azo.search(cfg, w, roots, tree_id0=1000, n_threads=8, dump=False)
-    out = _fit(E, E.run_engine(cfg, w, roots, tree_id0=1000, dump=False), ref)
+    out = _fit(E, E.run_engine(cfg, w, roots, tree_id0=1000, dump=False, **kw), ref)
     for k in RES_INT + RES_FP:
         assert np.array_equal(out[k], ref[k]), k
     assert np.array_equal(out["counters"][:7], ref["counters"][:7])
+    if fused:
+        assert out["counters"][7] == 1  # one launch for the whole search
+
+
+@pytest.mark.gpu
+def test_fused_search_in_chunks_equals_per_simulation_launches():
+    """A batch larger than one launch of the whole-search kernel covers (148 SMs x 16 tiles x 128 trees) is cut into chunks;
+    trees, counters and results must not depend on it."""
+    import enginelib as E
+    B, N = 148 * 16 * 128 + 1000, 12
+    cfg, roots = _q8(azo.continuous_config(n_rollouts=N)), G.pendulum_roots(B, seed=11)
+    rng = np.random.default_rng(6)
+    w = (rng.standard_normal(cfg.num_weights) * 0.08).astype(np.float32)
+    a = E.run_engine(cfg, w, roots, tree_id0=5, dump=False, fused=False)
+    b = E.run_engine(cfg, w, roots, tree_id0=5, dump=False, fused=True)
+    for k in RES_INT + RES_FP:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(a["counters"][:7], b["counters"][:7])
+    assert b["counters"][7] == 2
