@@ -24,7 +24,7 @@ EXPORTS = [
     "azg_search_discrete", "azg_search_continuous", "azg_cmax", "azg_root_results", "azg_search_host", "azg_status",
     "azg_rows", "azg_set_tapes", "azg_dump_tree_discrete", "azg_dump_tree_continuous", "azg_get_counters",
     "azg_head_dim", "azg_mlp_forward", "azg_env_step", "azg_profile_search", "azg_set_seed", "azg_selfplay_seed",
-    "azg_selfplay_step",
+    "azg_selfplay_step", "azg_fused_stats",
 ]
 
 
@@ -93,6 +93,7 @@ def load():
     L.azg_dump_tree_discrete.restype, L.azg_dump_tree_discrete.argtypes = C.c_int, [vp, i32, C.POINTER(DumpDiscrete)]
     L.azg_dump_tree_continuous.restype, L.azg_dump_tree_continuous.argtypes = C.c_int, [vp, i32, C.POINTER(DumpContinuous)]
     L.azg_get_counters.restype, L.azg_get_counters.argtypes = C.c_int, [vp, i32, C.POINTER(i64 * 8)]
+    L.azg_fused_stats.restype, L.azg_fused_stats.argtypes = C.c_int, [vp, C.POINTER(i64 * 8)]
     L.azg_profile_search.restype = C.c_int
     L.azg_profile_search.argtypes = [vp, i32, vp, vp, i32, i64, vp, C.POINTER(C.c_float * 3), C.POINTER(i32 * 3)]
     L.azg_head_dim.restype, L.azg_head_dim.argtypes = i32, [vp]

@@ -132,23 +132,33 @@ struct TreeParams {
 // correctly rounded quotient a / b (Markstein's final division step; b is a small integer, so the one exceptional divisor
 // pattern, an all-ones significand, cannot occur; 4e8 random cases checked against a / b on the CPU).  Zero, subnormal-range
 // and non-finite numerators take the ordinary division.
-__device__ __forceinline__ double div_small(double a, int b, const double* __restrict__ rcp) {
+__device__ __forceinline__ double div_small(double a, int b, const double* rcp, int tab_n) {
     const double fa = fabs(a);
-    if (b > AZG_TAB || !(fa > 1e-250 && fa < 1e250)) return a / (double)b;
-    const double y = __ldg(rcp + b);
+    if (b > tab_n || !(fa > 1e-250 && fa < 1e250)) return a / (double)b;
+    const double y = rcp[b];  // plain load: the table may sit in shared memory (whole-search kernel)
     const double q = __dmul_rn(a, y);
     const double r = __fma_rn(-q, (double)b, a);
     return __fma_rn(r, y, q);
 }
-__device__ __forceinline__ double sqrt_small(int n, const double* __restrict__ tab) {
-    return n <= AZG_TAB ? __ldg(tab + n) : sqrt((double)n);
+__device__ __forceinline__ double sqrt_small(int n, const double* tab, int tab_n) {
+    return n <= tab_n ? tab[n] : sqrt((double)n);
 }
+// The three small lookup tables of the select step.  k_step_* read them from global memory (L1-resident there); the whole-search
+// kernel, whose L1 is a few KB next to 215 KB of shared memory, keeps the first FUSED_TAB + 1 entries in shared memory
+// (continuous trees hold at most 255 rows, so visit counts + 1 stay below 256).
+#define FUSED_TAB 255
+struct Tabs {
+    const int32_t* pw;   // progressive-widening limits
+    const double* rcp;   // 1 / i
+    const double* sq;    // sqrt(i)
+    int n;               // largest index held
+};
 
 // ---- Philox4x32-10 (Salmon et al. SC'11); counter layout documented in DESIGN.md section 5 ---------
 struct u32x4 { uint32_t x, y, z, w; };
 
 __device__ __forceinline__ u32x4 philox4x32_10(u32x4 c, uint32_t k0, uint32_t k1) {
-#pragma unroll
+#pragma unroll 1  // rolled: the generator is inlined at half a dozen call sites of the tree kernels and never on a throughput path
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;

@@ -8,10 +8,12 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "../../include/azg.h"
@@ -60,6 +62,7 @@ struct azg_engine {
     int32_t* err = nullptr;
     float* wpack = nullptr;
     uint64_t* d_seed = nullptr;  // Philox key read by the kernels (azg_set_seed)
+    unsigned long long* stats = nullptr;  // cycle accounting of the whole-search kernel (azg_fused_stats)
     double* dtab = nullptr;      // rcp_tab[AZG_TAB + 1], sqrt_tab[AZG_TAB + 1] (common.cuh div_small)
     // AZG_FLAG_EVAL_Q8: int8 digit planes + f32 side table of the tensor-core evaluation kernel (qmlp.cuh)
     int8_t* qdigits = nullptr;
@@ -67,6 +70,13 @@ struct azg_engine {
     int qfl_count = 0;
     size_t qmlp_smem = 0;
     bool q8 = false;
+    // continuous tree: root edge tables + control blocks in ONE allocation, pinned in L2 (persisting access-policy window on every
+    // launch that walks trees): they are touched by every simulation of every tree (37.7 MB at 65536 trees, against 126 MB of L2),
+    // while the row tables stream through
+    void* hot_block = nullptr;
+    size_t hot_bytes = 0;
+    cudaLaunchAttribute l2attr;
+    int l2_on = 0;
     bool fused = false;  // AZG_FLAG_FUSED: the whole continuous search in one persistent kernel (qmlp2.cuh)
     // results staging (device) + pinned host staging for the *_host entry point
     float* r_actions = nullptr;
@@ -107,8 +117,8 @@ extern "C" void azg_destroy(azg_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
-    void* ptrs[] = {e->drows, e->dstate, e->crows, e->et, e->ctl, e->chead, e->pw_table, e->n_rows, e->draws,
-                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->dtab, e->qdigits, e->qfl, e->r_actions,
+    void* ptrs[] = {e->drows, e->dstate, e->crows, e->hot_block, e->chead, e->pw_table, e->n_rows, e->draws,
+                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qfl, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -164,7 +174,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     e->q8 = (c.flags & AZG_FLAG_EVAL_Q8) != 0;
     if (e->q8) {
         e->qfl_count = (c.state_dim * H + H + (c.n_hidden - 1) * 2 * H + H * e->PO_PAD + e->PO_PAD + 3) / 4 * 4;
-        e->qmlp_smem = qmlp2_smem_bytes(c.n_hidden - 1, e->qfl_count);
+        e->qmlp_smem = qmlp2_smem_bytes(c.n_hidden - 1, e->qfl_count, (c.flags & AZG_FLAG_FUSED) != 0);
         if (H != 128 || c.n_hidden < 2 || c.n_hidden > 3 || e->PO_PAD > Q2_MAX_PO || e->qmlp_smem > (size_t)prop.sharedMemPerBlockOptin ||
             prop.major != 10) {
             delete e;
@@ -206,8 +216,37 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
         ALLOC(dstate, B * R * 4);
     } else {
         ALLOC(crows, B * R);
-        ALLOC(et, B * CROOT_MAX_KIDS);
-        ALLOC(ctl, B);
+        {
+            e->hot_bytes = B * (CROOT_MAX_KIDS * sizeof(CHot) + sizeof(CCtl));
+            char* hb = nullptr;
+            cudaError_t _e = cudaMalloc(&hb, e->hot_bytes);
+            if (_e != cudaSuccess) {
+                std::string m = cudaGetErrorString(_e);
+                azg_destroy(e);
+                return fail(AZG_ECUDA, "cudaMalloc hot block: " + m);
+            }
+            e->hot_block = hb;
+            e->et = reinterpret_cast<CHot*>(hb);
+            e->ctl = reinterpret_cast<CCtl*>(hb + B * CROOT_MAX_KIDS * sizeof(CHot));
+            const size_t persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize), win_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
+            if (persist_max > 0 && win_max > 0 && !getenv("AZG_NO_L2_PERSIST")) {
+                const size_t want = std::min(persist_max, e->hot_bytes);
+                size_t have = 0;
+                cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+                if (have < want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+                cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+                memset(&e->l2attr, 0, sizeof e->l2attr);
+                e->l2attr.id = cudaLaunchAttributeAccessPolicyWindow;
+                cudaAccessPolicyWindow& w = e->l2attr.val.accessPolicyWindow;
+                w.base_ptr = hb;
+                w.num_bytes = std::min(e->hot_bytes, win_max);
+                w.hitRatio = (float)std::min(1.0, (double)have / (double)w.num_bytes);
+                w.hitProp = cudaAccessPropertyPersisting;
+                w.missProp = cudaAccessPropertyStreaming;
+                e->l2_on = have > 0;
+                cudaGetLastError();
+            }
+        }
         ALLOC(chead, B * R * e->HS);
         ALLOC(pw_table, pwt.size());
         ALLOC(path, B * R);
@@ -222,6 +261,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(err, 1);
     ALLOC(wpack, (size_t)e->wcount);
     ALLOC(d_seed, 1);
+    ALLOC(stats, 8);
     ALLOC(dtab, 2 * (AZG_TAB + 1));
     if (e->q8) {
         ALLOC(qdigits, (size_t)(c.n_hidden - 1) * 3 * QMLP_PLANE);
@@ -230,6 +270,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(r_actions, B * e->cmax); ALLOC(r_counts, B * e->cmax); ALLOC(r_Q, B * e->cmax); ALLOC(r_Vt, B); ALLOC(r_nchild, B);
 #undef ALLOC
     CK(cudaMemset(e->err, 0, sizeof(int32_t)));
+    CK(cudaMemset(e->stats, 0, 8 * sizeof(unsigned long long)));
     CK(cudaMemcpy(e->d_seed, &c.seed, sizeof(uint64_t), cudaMemcpyHostToDevice));
     {
         std::vector<double> tab(2 * (AZG_TAB + 1), 0.0);
@@ -419,7 +460,22 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     m.ctl = e->ctl; m.et = e->et; m.gamma_f32 = (float)c.gamma;
     m.head_dim = azg_head_dim(e);
     m.qdigits = e->qdigits; m.qfl = e->qfl; m.qfl_count = e->qfl_count;
+    m.stats = e->stats;
     return m;
+}
+
+// kernel launch carrying the persisting-L2 window of the hot block (recorded into graph nodes under stream capture)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(const azg_engine* e, void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = const_cast<cudaLaunchAttribute*>(&e->l2attr);
+    cfg.numAttrs = e->l2_on ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <int H, int S, int ACT>
@@ -427,8 +483,7 @@ static cudaError_t launch_mlp_t(const azg_engine* e, const MlpParams& m, cudaStr
     if (set_attr) return cudaFuncSetAttribute(k_mlp<H, S, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->mlp_smem);
     const int units = (m.n + MLP_UNIT - 1) / MLP_UNIT;
     const int grid = std::max(1, std::min((units + MLP_NGRP - 1) / MLP_NGRP, e->sm_count));
-    k_mlp<H, S, ACT><<<grid, MLP_THREADS(H), e->mlp_smem, st>>>(m);
-    return cudaGetLastError();
+    return launch_ex(e, k_mlp<H, S, ACT>, grid, MLP_THREADS(H), e->mlp_smem, st, m);
 }
 
 template <int S, int ACT, int NL>
@@ -441,8 +496,7 @@ static cudaError_t launch_qmlp_t(const azg_engine* e, const MlpParams& m, cudaSt
     const int grid = std::max(1, std::min((m.n + 127) / 128, e->sm_count));
     TreeParams none;
     memset(&none, 0, sizeof none);
-    k_qmlp2<S, ACT, NL, false><<<grid, Q2_THREADS, e->qmlp_smem, st>>>(m, none, 0, 0, 0);
-    return cudaGetLastError();
+    return launch_ex(e, k_qmlp2<S, ACT, NL, false>, grid, Q2_THREADS, e->qmlp_smem, st, m, none, 0, 0, 0);
 }
 
 // whole-search kernel (AZG_FLAG_FUSED): one persistent launch per chunk of at most sm_count x Q2_MAX_TILES x 128 trees
@@ -452,9 +506,8 @@ static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const
     for (int lo = 0; lo < p.B; lo += chunk) {
         const int hi = std::min(p.B, lo + chunk);
         const int grid = std::max(1, std::min((hi - lo + 127) / 128, e->sm_count));
-        k_qmlp2<S, ACT, NL, true><<<grid, Q2_FUSED_THREADS, e->qmlp_smem, st>>>(m, p, N, lo, hi);
+        cudaError_t ce = launch_ex(e, k_qmlp2<S, ACT, NL, true>, grid, Q2_FUSED_THREADS, e->qmlp_smem, st, m, p, N, lo, hi);
         ++*launches;
-        cudaError_t ce = cudaGetLastError();
         if (ce != cudaSuccess) return ce;
     }
     return cudaSuccess;
@@ -490,9 +543,7 @@ static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStrea
 
 template <bool BK, bool SEL>
 static cudaError_t launch_step_continuous(const azg_engine* e, const TreeParams& p, cudaStream_t st) {
-    (void)e;
-    k_step_continuous<BK, SEL><<<(p.B + 127) / 128, 128, 0, st>>>(p);
-    return cudaGetLastError();
+    return launch_ex(e, k_step_continuous<BK, SEL>, (p.B + 127) / 128, 128, 0, st, p);
 }
 
 // per-launch CUDA-event timing used by azg_profile_search (classes: 0 tree step, 1 evaluation, 2 setup)
@@ -785,6 +836,17 @@ extern "C" int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]) {
     }
     out[0] = (int64_t)nb * e->last_N;
     out[7] = e->launches;
+    return AZG_OK;
+}
+
+extern "C" int azg_fused_stats(azg_engine* e, int64_t out[8]) {
+    if (!e || !out) return fail(AZG_EINVAL, "null argument");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[8];
+    CK(cudaMemcpy(h, e->stats, sizeof h, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(e->stats, 0, sizeof h));
+    for (int k = 0; k < 8; ++k) out[k] = (int64_t)h[k];
     return AZG_OK;
 }
 

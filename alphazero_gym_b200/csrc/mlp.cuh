@@ -50,6 +50,10 @@ struct MlpParams {
     const int8_t* qdigits;
     const float* qfl;
     int32_t qfl_count;  // floats in qfl (multiple of 4)
+    // whole-search kernel: cycle accounting, summed over CTAs (azg_fused_stats): [0] kernel cycles, [1] epilogue warp 0 waiting
+    // for the next network inputs of a tile (xready: tree latency NOT hidden), [2] tree warp 0 of slot 0 waiting for an
+    // evaluation (hfull: slack), [3] the same warp inside finish + backup + select + expansion, [4] CTAs
+    unsigned long long* stats;
 };
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP / SYNCS) --------------
@@ -72,6 +76,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// the same with a suspend-time hint (ns): the warp sleeps inside the instruction until the phase completes or the time is up,
+// instead of coming back every few hundred cycles to spin (a quarter of all issued instructions of the first whole-search kernel
+// were wait loops, profiles/r1f)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
         : "memory");
     return ok != 0;
 }

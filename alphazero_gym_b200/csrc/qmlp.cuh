@@ -21,9 +21,9 @@
 // bounded spin: a protocol error traps (the launch fails with an error) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s
+    int spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++spins > (1 << 22)) __trap();  // seconds
     }
 }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {  // no swizzle, K-major, LBO 2048 B, SBO 128 B, descriptor version 1

@@ -29,14 +29,21 @@
 #define Q2_EPI_THREADS 512
 #define Q2_THREADS 768                // 16 epilogue warps + the MMA warpgroup + the post-processing warpgroup (registers rebalanced with setmaxnreg)
 #define Q2_FUSED_THREADS 896          // whole-search kernel: 16 epilogue warps + the MMA warpgroup + one tree warpgroup per tile slot
+#ifndef Q2F_EPI_REGS
+#define Q2F_EPI_REGS 96               // whole-search kernel: 512 x 96 + 128 x 24 + 256 x 48 = 896 x 72, the CTA's register pool at launch
+#define Q2F_TREE_REGS 48
+#endif
+#define Q2_STR2(x) #x
+#define Q2_STR(x) Q2_STR2(x)
 #define Q2_MAX_TILES 16               // whole-search kernel: tiles per CTA and launch (engine.cu cuts larger batches into chunks)
 #define Q2_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24))  // s8 x s8 -> s32, K-major, N = 64, M = 128
 #define Q2_ACC_COLS 192               // accumulator window of a tile: PA | PB | PC, 64 columns each
 #define Q2_SCRATCH_COL 384            // head partial sums of tile T: columns 384 + 64 T + 16 cq + c
 #define Q2_MAX_PO 16
 
-__host__ __device__ inline size_t qmlp2_smem_bytes(int NL, int qfl_count) {
-    return (size_t)NL * 3 * QMLP_PLANE + 2 * 3 * QMLP_PLANE + (size_t)qfl_count * 4 + 2 * 4 * 128 * 4 + 1024;
+#define Q2_TAB_BYTES ((FUSED_TAB + 1) * (8 + 8 + 4))  // whole-search kernel: rcp, sqrt and progressive-widening tables in shared memory
+__host__ __device__ inline size_t qmlp2_smem_bytes(int NL, int qfl_count, bool fused = false) {
+    return (size_t)NL * 3 * QMLP_PLANE + 2 * 3 * QMLP_PLANE + (size_t)qfl_count * 4 + 2 * 4 * 128 * 4 + 1024 + (fused ? Q2_TAB_BYTES : 0);
 }
 // row of the digit planes that holds output j: half h = (j/16)%2, D column of the half = 16*(j/32) + j%16
 __host__ __device__ inline int qmlp_perm_row(int j) { return 64 * ((j >> 4) & 1) + 16 * (j >> 5) + (j & 15); }
@@ -230,6 +237,9 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
     int8_t* sA = sB + (size_t)NL * 3 * QMLP_PLANE;                   // [2][3][8][128][16]
     float* fl = reinterpret_cast<float*>(sA + 2 * 3 * QMLP_PLANE);   // W0t[S][H], b0[H], NL x (cw, bias)[H], Wh[H][PO_PAD], bh[PO_PAD]
     float* pmax = fl + p.qfl_count;                                  // [2][4][128]
+    double* s_rcp = reinterpret_cast<double*>(pmax + 2 * 4 * 128);   // whole-search kernel: [FUSED_TAB + 1] each
+    double* s_sq = s_rcp + FUSED_TAB + 1;
+    int32_t* s_pw = reinterpret_cast<int32_t*>(s_sq + FUSED_TAB + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -271,15 +281,25 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         for (uint32_t o = 0; o < bytesB; o += 32768u) bulk_g2s(sB + o, p.qdigits + o, min(32768u, bytesB - o), &wbar);
         bulk_g2s(fl, p.qfl, bytesF, &wbar);
     }
+    if (FUSED) {
+        for (int i = tid; i <= FUSED_TAB; i += blockDim.x) {
+            s_rcp[i] = tp.rcp_tab[i];
+            s_sq[i] = tp.sqrt_tab[i];
+            s_pw[i] = i < p.R ? tp.pw_table[i] : 0;  // the table has max_rollouts + 2 = R entries
+        }
+        __syncthreads();
+    }
     mbar_wait(&wbar, 0);
 
     if (FUSED && warp >= 20) {
         // ---- tree warpgroup of tile slot w: finishes the evaluated rows of its tiles and advances their trees
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " Q2_STR(Q2F_TREE_REGS) ";");
         const int w = (warp - 20) >> 2, lg = warp & 3, r = lg * 32 + lane;
         const float* bh = fl + S * 128 + 128 + NL * 2 * 128 + 128 * p.PO_PAD;
         uint32_t hph = 0, nev = 0;
         int ev_row = 0;
+        long long cyc_wait = 0, cyc_work = 0;
+        const Tabs tabs = {s_pw, s_rcp, s_sq, FUSED_TAB};
 #pragma unroll 1
         for (int t = w; t < ntiles; t += 2) {  // MCTSContinuous.initialize_search for every tree of the tile
             const int row0 = row_begin + t * th;
@@ -300,24 +320,34 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
                 double lr = 0.0;
                 if (valid) {
                     const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
-                    const uint4 c0 = cp[0], c1 = cp[1];
+                    const uint4 c0 = cp[0], c1 = cp[1], c2 = cp[2];
                     leafw = (int)c0.z;
                     lr = __hiloint2double((int)c1.w, (int)c1.z);
                     need = (leafw & LEAF_EVAL) != 0;
+                    c_prefetch(tp, gr, c0, c2);  // HBM -> L2 while the tile is being evaluated
                 }
+                const long long c0 = clock64();
                 mbar_wait(&hfull[w], hph);
                 hph ^= 1u;
+                const long long c1 = clock64();
                 tc_fence_after();
                 if (lg * 32 < nv) q2_finish_tile(p, tb, bh, lg, w, need, gr, leafw, lr, hfree, nev, ev_row);
                 else mbar_arrive(&hfree[w]);
                 if (valid) {
                     if (s == 0) c_root_insert(tp, gr);         // the add_pw_action(root) before the loop (mcts.py:673)
-                    c_step(tp, gr, s > 0, s + 1 < n_evals);    // backup of simulation s, descent + expansion of simulation s + 1
+                    c_step(tp, tabs, gr, s > 0, s + 1 < n_evals);  // backup of simulation s, descent + expansion of simulation s + 1
                 }
+                __syncwarp();
                 if (s + 1 < n_evals) mbar_arrive(&xready[t]);  // releases X[gr] to the epilogue warps
+                cyc_wait += c1 - c0;
+                cyc_work += clock64() - c1;
             }
         }
         if (nev) p.evals[ev_row] += nev;
+        if (tid == 640 && p.stats) {
+            atomicAdd(p.stats + 2, (unsigned long long)cyc_wait);
+            atomicAdd(p.stats + 3, (unsigned long long)cyc_work);
+        }
     } else if (warp >= 20) {
         // ---- post-processing warpgroup: warp 20 + lg finishes the rows of row group lg, tile after tile
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -392,7 +422,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         }
     } else {
         // ---- epilogue warps
-        if (FUSED) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");  // 512 x 96 + 128 x 24 + 256 x 48 = 896 x 72, the CTA's pool at launch
+        if (FUSED) asm volatile("setmaxnreg.inc.sync.aligned.u32 " Q2_STR(Q2F_EPI_REGS) ";");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");       // 512 x 104 + 128 x 24 + 128 x 40 = 768 x 80
         Q2Ctx c;
         c.W0 = fl;
@@ -406,6 +436,8 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         c.tb = tb;
         c.lg = warp & 3; c.cq = warp >> 2;
         c.r = c.lg * 32 + lane;
+        long long cyc_x = 0;
+        const long long cyc_begin = clock64();
         uint32_t fullph = 0;  // bit T: parity of the next wait on full[T]
         uint32_t hfph = 0;    // bit T: parity of the next wait on hfree[T]
 #pragma unroll 1
@@ -418,7 +450,11 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
             for (int T = 0; T < nt; ++T) {
                 const int row0 = row_begin + (t0 + T) * th;
                 const int nv = max(0, min(th, row_end - row0));
-                if (FUSED) mbar_wait(&xready[t0 + T], (uint32_t)s & 1u);  // the tile's trees have written their next network inputs
+                if (FUSED) {  // the tile's trees have written their next network inputs
+                    const long long c0 = clock64();
+                    mbar_wait(&xready[t0 + T], (uint32_t)s & 1u);
+                    cyc_x += clock64() - c0;
+                }
                 const float cx = q2_layer0<S, ACT>(c, p, T, c.lg * 32 < nv, row0 + c.r, c.r < nv);
                 if (T == 0) cx0 = cx; else cx1 = cx;
             }
@@ -489,6 +525,11 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
                     }
                 }
             }
+        }
+        if (FUSED && tid == 0 && p.stats) {
+            atomicAdd(p.stats + 0, (unsigned long long)(clock64() - cyc_begin));
+            atomicAdd(p.stats + 1, (unsigned long long)cyc_x);
+            atomicAdd(p.stats + 4, 1ull);
         }
     }
     tc_fence_before();

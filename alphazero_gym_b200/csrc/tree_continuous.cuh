@@ -170,32 +170,44 @@ __global__ void k_root_insert_continuous(const TreeParams p) {
 #define KIND_TERMINAL 2  // the trace ended on an existing terminal node
 #define KIND_ERROR 3
 
-// UCT over up to 16 children whose hot sectors are gathered through `hot_of(j)`; returns the selected index
-// (mcts.py:729-741 + helpers.argmax + epsilon_greedy)
-template <typename HotOf>
-__device__ __forceinline__ int uct_select(const TreeParams& p, int64_t tree, int nk, uint32_t cur_nn, float cur_V, int& draws, bool& nan,
-                                          HotOf hot_of) {
-    const double sq = sqrt_small((int)cur_nn + 1, p.sqrt_tab);
+// UCT over the nk <= 16 children of a node; returns the selected index (mcts.py:729-741 + helpers.argmax + epsilon_greedy).
+// Child j's hot sector is et[j] for the root and rows[kids[j]] otherwise.  Only the two fields the score needs (W, n) are
+// gathered, four children per round trip; the score loop is ROLLED (the four gathered pairs rotate through one set of
+// registers) and there is one instance of it for root and inner nodes: the first version unrolled 16 children x 2 call sites
+// x two inlined IEEE divisions into 5000 SASS instructions, which the whole-search kernel (qmlp2.cuh) paid for in instruction
+// fetch on the evaluation warps.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ const CHot* child_hot(const CHot* et, const CRow* rows, const uint32_t kw[4], bool is_root, int j) {
+    return is_root ? et + j : reinterpret_cast<const CHot*>(rows + list_byte(kw, j));
+}
+__device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, int64_t tree, int nk, uint32_t cur_nn, float cur_V, int& draws,
+                                          bool& nan, const CHot* et, const CRow* rows, const uint32_t kw[4], bool is_root) {
+    const double sq = sqrt_small((int)cur_nn + 1, tb.sq, tb.n);
     double best = -CUDART_INF;
     uint32_t win = 0;
+#pragma unroll 1
+    for (int w0 = 0; w0 < nk; w0 += 4) {
+        double W[4];
+        int n[4];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        if (w * 4 < nk) {
-            CHot c[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) c[i] = hot_of(w * 4 + i < nk ? w * 4 + i : 0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int j = w * 4 + i;
-                if (j < nk) {
-                    const int n = c[i].n_e;
-                    const double Q = n > 0 ? div_small(c[i].W, n, p.rcp_tab) : (double)cur_V;
-                    const double u = Q + p.c_uct * div_small(sq, n + 1, p.rcp_tab);  // mcts.py:731-732
-                    nan |= (u != u);
-                    if (u > best) { best = u; win = 1u << j; }
-                    else if (u == best) win |= 1u << j;
-                }
-            }
+        for (int i = 0; i < 4; ++i) {
+            const CHot* h = child_hot(et, rows, kw, is_root, w0 + i < nk ? w0 + i : w0);
+            W[i] = h->W;
+            n[i] = h->n_e;
+            // the second sector of an inner node's child (its child list + env state) is the other half of the same 64 B DRAM
+            // burst: requested now, it is there when the descent enters the winner
+            if (!is_root) prefetch_l1(reinterpret_cast<const char*>(h) + 32);
+        }
+        const int m = min(4, nk - w0);
+#pragma unroll 1
+        for (int i = 0; i < m; ++i) {
+            const double Q = n[0] > 0 ? div_small(W[0], n[0], tb.rcp, tb.n) : (double)cur_V;
+            const double u = Q + p.c_uct * div_small(sq, n[0] + 1, tb.rcp, tb.n);  // mcts.py:731-732
+            nan |= (u != u);
+            if (u > best) { best = u; win = 1u << (w0 + i); }
+            else if (u == best) win |= 1u << (w0 + i);
+            W[0] = W[1]; W[1] = W[2]; W[2] = W[3];
+            n[0] = n[1]; n[1] = n[2]; n[2] = n[3];
         }
     }
     bool random_pick = false;
@@ -203,17 +215,29 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, int64_t tree, int
         const double x = (double)u32_to_unit(rng_select_u32(p, tree, draws++));
         random_pick = x < p.epsilon;
     }
-    if (random_pick) return u32_to_index(rng_select_u32(p, tree, draws++), nk);
-    // random.choice(winners): the draw is consumed even when there is a single winner
-    const int nw = __popc(win);
+    // random.choice(winners) / random.randint: the draw is consumed even when there is a single winner
+    const int nw = random_pick ? nk : __popc(win);
     const int pick = nw > 1 ? u32_to_index(rng_select_u32(p, tree, draws), nw) : 0;
     ++draws;
+    if (random_pick) return pick;
     return nw > 0 ? (int)__fns(win, 0, pick + 1) : 0;
+}
+
+// Whole-search kernel: while a tree thread waits for its tile's evaluation it pulls the lines its next step is known to touch
+// from HBM into L2 (the control block's path rows for the backup, the root edge table for the first UCT scan).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void c_prefetch(const TreeParams& p, int t, const uint4 c0, const uint4 c2) {
+    const CRow* rows = p.crows + (size_t)t * p.R;
+    const CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
+    const int depth = (int)((c0.x >> 8) & 0xFFu), root_nk = (int)((c0.x >> 16) & 0xFFu);
+    for (int j = 0; j < root_nk; j += 4) prefetch_l2(et + j);  // 128 B lines
+    const uint32_t pw[4] = {c2.x, c2.y, c2.z, c2.w};
+    for (int i = 1; i < min(depth, 16); ++i) prefetch_l2(rows + list_byte(pw, i));
 }
 
 // one simulation step of tree t: backup of the previous simulation (BACKUP), then descent + expansion of the next (SELECT).
 // Shared by k_step_continuous (one launch per simulation) and the whole-search kernel k_search_fused (fused.cuh).
-__device__ __forceinline__ void c_step(const TreeParams& p, int t, const bool BACKUP, const bool SELECT) {
+__device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int t, const bool BACKUP, const bool SELECT) {
     CRow* rows = p.crows + (size_t)t * p.R;
     CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
     uint8_t* path_ovf = p.path + (size_t)t * p.R;
@@ -223,6 +247,15 @@ __device__ __forceinline__ void c_step(const TreeParams& p, int t, const bool BA
     CCtl c = load_ctl(p.ctl + t);
     uint32_t pathw[4];
     memcpy(pathw, c.path, 16);
+    // The step is a chain of dependent loads (profiles/r1e: 13 long-scoreboard stall cycles per issued instruction), so every
+    // line whose address is known now is requested now: the rows of the recorded path (backup), the root edge table (backup
+    // of the root edge + first UCT scan) and the root's policy head if the root is about to be widened.
+    {
+        const int d = BACKUP ? (int)c.depth : 0;
+        for (int i = 1; i < min(d, 16); ++i) prefetch_l1(rows + list_byte(pathw, i));
+        for (int j = 0; j < (int)c.root_nk; j += 4) prefetch_l1(et + j);
+        if (SELECT && tb.pw[c.root_nn + (d > 0 ? 1 : 0)] - (int)c.root_nk > 0) prefetch_l1(p.chead + (size_t)t * p.R * p.HS);
+    }
 
     if (BACKUP) {
         // backprop (mcts.py:241-267) along the recorded path.  leafR already holds r_leaf + gamma*V_leaf
@@ -254,17 +287,14 @@ __device__ __forceinline__ void c_step(const TreeParams& p, int t, const bool BA
         int jsel = 0;
         while (true) {
             ++levels;
-            if (p.pw_table[cur_nn] - nk > 0) { kind = KIND_INSERT; break; }  // states.py:252-275
-            CHot sh;
-            if (cur == 0) {
-                jsel = uct_select(p, tree, nk, cur_nn, cur_V, draws, nan, [&](int j) { return load_hot(et + j); });
-                sh = load_hot(et + jsel);
-            } else {
-                jsel = uct_select(p, tree, nk, cur_nn, cur_V, draws, nan, [&](int j) { return load_hot(rows + list_byte(kw, j)); });
-                sh = load_hot(rows + list_byte(kw, jsel));
-            }
-            scanned += nk;
+            if (tb.pw[cur_nn] - nk > 0) { kind = KIND_INSERT; break; }  // states.py:252-275
+            jsel = uct_select(p, tb, tree, nk, cur_nn, cur_V, draws, nan, et, rows, kw, cur == 0);
             sel = list_byte(kw, jsel);
+            const CHot sh = load_hot(child_hot(et, rows, kw, cur == 0, jsel));  // the line was gathered a moment ago
+            // requested together with sh (one round trip instead of two); used only if the descent enters the node
+            const CSec1 s1 = load_sec1(rows + sel);
+            prefetch_l1(p.chead + ((size_t)t * p.R + sel) * p.HS);  // the node's cached policy head, read if the node is widened
+            scanned += nk;
             if (depth == 0) c.j0 = (uint8_t)jsel;
             if (depth < 16) set_list_byte(pathw, depth, sel); else path_ovf[depth] = (uint8_t)sel;
             ++depth;
@@ -274,7 +304,6 @@ __device__ __forceinline__ void c_step(const TreeParams& p, int t, const bool BA
             cur_nn = sh.nn_flags & CROW_NMASK;
             cur_V = sh.V;
             if (sh.nn_flags & CROW_TERMINAL) { kind = KIND_TERMINAL; leaf_r = sh.r; (void)from_root; break; }
-            const CSec1 s1 = load_sec1(rows + cur);
             kw[0] = s1.kw[0]; kw[1] = s1.kw[1]; kw[2] = s1.kw[2]; kw[3] = s1.kw[3];
             nk = (int)(kw[3] >> 24);
             cur_th = s1.th; cur_thdot = s1.thdot;
@@ -349,7 +378,8 @@ __device__ __forceinline__ void c_step(const TreeParams& p, int t, const bool BA
 template <bool BACKUP, bool SELECT>
 __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < p.B) c_step(p, t, BACKUP, SELECT);
+    const Tabs tb = {p.pw_table, p.rcp_tab, p.sqrt_tab, AZG_TAB};
+    if (t < p.B) c_step(p, tb, t, BACKUP, SELECT);
 }
 
 // numpy pairwise summation for n <= 128 (np.sum in get_on_policy_value_target, mcts.py:111)

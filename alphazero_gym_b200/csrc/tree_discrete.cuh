@@ -88,14 +88,14 @@ __global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
         bool nan = false;
         while (true) {
             // UCT_a = Q_a + prior_a*c_uct*(sqrt(node.n+1)/(n_a+1))   (mcts.py:483-484)
-            const double sq = sqrt_small(row.node_n + 1, p.sqrt_tab);
+            const double sq = sqrt_small(row.node_n + 1, p.sqrt_tab, AZG_TAB);
             double u[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int n = row.n_e[i];
-                const double Q = n > 0 ? div_small(row.W[i], n, p.rcp_tab) : (double)row.V;
+                const double Q = n > 0 ? div_small(row.W[i], n, p.rcp_tab, AZG_TAB) : (double)row.V;
                 const double pc = p.puct_f32 ? (double)__fmul_rn(row.prior[i], (float)p.c_uct) : (double)row.prior[i] * p.c_uct;
-                u[i] = Q + pc * div_small(sq, n + 1, p.rcp_tab);
+                u[i] = Q + pc * div_small(sq, n + 1, p.rcp_tab, AZG_TAB);
             }
             nan |= (u[0] != u[0]) || (u[1] != u[1]);
             bool random_pick = false;

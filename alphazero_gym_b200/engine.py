@@ -43,7 +43,7 @@ class EngineConfig:
     seed: int = 34
     use_graph: bool = True
     eval_q8: bool = False  # AZG_FLAG_EVAL_Q8: hidden x hidden layers on tcgen05 as exact int8-sliced products (include/azg.h)
-    fused: Optional[bool] = None  # AZG_FLAG_FUSED: whole search in one persistent kernel; None = on where supported (continuous + eval_q8)
+    fused: Optional[bool] = None  # AZG_FLAG_FUSED: whole search in one persistent kernel; None = the default (off)
 
     def c(self) -> AzgConfig:
         return AzgConfig(self.variant, self.max_rollouts, self.max_trees, self.num_actions, self.num_components,
@@ -54,8 +54,7 @@ class EngineConfig:
                          | (_cabi.FLAG_FUSED if self.is_fused() else 0), self.seed)
 
     def is_fused(self) -> bool:
-        supported = bool(self.eval_q8) and self.variant == CONTINUOUS
-        return supported if self.fused is None else bool(self.fused)
+        return False if self.fused is None else bool(self.fused)  # opt-in until it beats the per-simulation launches
 
 
 def flatten_state_dict(sd) -> np.ndarray:
@@ -236,6 +235,14 @@ class SearchEngine:
         check(self._lib.azg_get_counters(self._h, B, C.byref(arr)))
         names = ("sims", "levels", "children_scanned", "pw_inserts", "evals", "rng_draws", "terminal_leaf_sims", "launches")
         return dict(zip(names, [int(v) for v in arr]))
+
+    def fused_stats(self) -> Dict[str, float]:
+        """Cycle accounting of the whole-search kernel since the last call (azg_fused_stats), as fractions of the kernel time."""
+        arr = (C.c_int64 * 8)()
+        check(self._lib.azg_fused_stats(self._h, C.byref(arr)))
+        tot = max(1, int(arr[0]))
+        return {"ctas": int(arr[4]), "kernel_cycles_per_cta": tot / max(1, int(arr[4])), "eval_waits_for_trees": arr[1] / tot,
+                "trees_wait_for_eval": arr[2] / tot, "tree_work": arr[3] / tot}
 
     # ---- standalone kernels (known-answer tests) ---------------------------------------------------------
     def mlp_forward(self, x: np.ndarray):

@@ -66,7 +66,7 @@ def make_weights(variant: str) -> np.ndarray:
     return init_policy_weights(34, 3, 128, 3, 6)
 
 
-def engine_config(variant: str, B: int, N: int, device: int, q8: bool = False):
+def engine_config(variant: str, B: int, N: int, device: int, q8: bool = False, fused=None):
     from alphazero_gym_b200.engine import EngineConfig
     from alphazero_gym_b200._cabi import ACT_ELU, ACT_RELU, CONTINUOUS, DISCRETE
     if variant == "discrete":  # run_discrete.yaml / MCTSDiscrete.yaml / DiscretePolicy.yaml
@@ -74,7 +74,7 @@ def engine_config(variant: str, B: int, N: int, device: int, q8: bool = False):
                             activation=ACT_RELU, c_uct=1.5, gamma=1.0, epsilon=0.1, device=device, seed=34, eval_q8=q8)
     return EngineConfig(variant=CONTINUOUS, max_rollouts=N, max_trees=B, num_components=2, state_dim=3, hidden=128, n_hidden=3,
                         activation=ACT_ELU, c_uct=0.05, c_pw=1.0, kappa=0.5, gamma=1.0, epsilon=0.0, action_bound=2.0,
-                        device=device, seed=34, eval_q8=q8)
+                        device=device, seed=34, eval_q8=q8, fused=fused)
 
 
 def oracle_config(variant: str, N: int):
@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--workload", default="pendulum_65536x100", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused", default="auto", choices=["auto", "on", "off"],
+                    help="whole-search persistent kernel (AZG_FLAG_FUSED); auto = the engine's default")
     ap.add_argument("--eval", default="q8", choices=["fp32", "q8"],
                     help="leaf evaluation arithmetic: int8-sliced tcgen05 products (qmlp2.cuh, default) or FP32 FMA (mlp.cuh)")
     args = ap.parse_args()
@@ -239,7 +241,7 @@ def main():
     tree_id0 = rank * B  # global tree ids: shard r owns trees [r*B, (r+1)*B)
     roots_h = make_roots(variant, B * world)[rank * B:(rank + 1) * B].copy()
     weights = make_weights(variant)
-    eng = SearchEngine(engine_config(variant, B, N, local, q8=args.eval == "q8"))
+    eng = SearchEngine(engine_config(variant, B, N, local, q8=args.eval == "q8", fused={"auto": None, "on": True, "off": False}[args.fused]))
     eng.set_weights(weights)
     roots_d = torch.from_numpy(roots_h).cuda()
 
