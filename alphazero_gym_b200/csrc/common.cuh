@@ -104,8 +104,12 @@ struct TreeParams {
     // continuous tables
     CRow* crows;      // [B][R]
     float* chead;     // [B][R][HS]  mu[K], sigma[K], prob[K]
-    CHot* et;         // [B][16]  root edge table: hot sectors of the root's children, insertion order
-    CCtl* ctl;        // [B]      control blocks
+    // Tree-INTERLEAVED tables (BS = max_trees is the stride): a warp advances 32 consecutive trees in lockstep, so entry j of tree t
+    // sits next to entry j of tree t + 1 and a warp-wide access touches 4 (control chunk) or 8 (edge) lines instead of 32 --
+    // the tree kernels are bound by L1 tag lookups of per-thread scattered accesses, not by HBM (profiles/README.md r1f)
+    CHot* et;         // [16][BS]  root edge table: hot sectors of the root's children, insertion order; child j of tree t = et[j * BS + t]
+    uint4* ctl;       // [4][BS]   control blocks (CCtl) as four 16-byte chunk planes: chunk k of tree t = ctl[k * BS + t]
+    int32_t BS;
     const int32_t* pw_table;  // [max_rollouts + 2]  ceil(c_pw * (n+1)^kappa), built on the host
     const double* rcp_tab;    // [AZG_TAB + 1]  1.0 / i  (host-built, correctly rounded), see div_small
     const double* sqrt_tab;   // [AZG_TAB + 1]  sqrt(i)

@@ -51,7 +51,7 @@ struct azg_engine {
     double* dstate = nullptr;
     CRow* crows = nullptr;
     CHot* et = nullptr;
-    CCtl* ctl = nullptr;
+    uint4* ctl = nullptr;  // [4][max_trees] chunk planes of the control blocks (common.cuh)
     float* chead = nullptr;
     int32_t *pw_table = nullptr, *n_rows = nullptr, *draws = nullptr, *leaf = nullptr;
     uint8_t* path = nullptr;
@@ -227,7 +227,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
             }
             e->hot_block = hb;
             e->et = reinterpret_cast<CHot*>(hb);
-            e->ctl = reinterpret_cast<CCtl*>(hb + B * CROOT_MAX_KIDS * sizeof(CHot));
+            e->ctl = reinterpret_cast<uint4*>(hb + B * CROOT_MAX_KIDS * sizeof(CHot));
             const size_t persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize), win_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
             if (persist_max > 0 && win_max > 0 && !getenv("AZG_NO_L2_PERSIST")) {
                 const size_t want = std::min(persist_max, e->hot_bytes);
@@ -439,7 +439,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.gamma_f32 = (float)c.gamma; p.action_bound = c.action_bound;
     p.seedp = e->d_seed; p.tree_id0 = tree_id0;
     p.drows = e->drows; p.dstate = e->dstate;
-    p.crows = e->crows; p.et = e->et; p.ctl = e->ctl; p.chead = e->chead;
+    p.crows = e->crows; p.et = e->et; p.ctl = e->ctl; p.BS = e->cfg.max_trees; p.chead = e->chead;
     p.pw_table = e->pw_table;
     p.rcp_tab = e->dtab; p.sqrt_tab = e->dtab + AZG_TAB + 1;
     p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path;
@@ -457,10 +457,16 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     m.variant = c.variant; m.A = c.num_actions; m.K = c.num_components; m.R = e->R; m.HS = e->HS;
     m.ls_min = c.log_std_min; m.ls_max = c.log_std_max;
     m.leaf = e->leaf; m.drows = e->drows; m.crows = e->crows; m.chead = e->chead; m.evals = e->ctr + (size_t)3 * n;
-    m.ctl = e->ctl; m.et = e->et; m.gamma_f32 = (float)c.gamma;
+    m.ctl = e->ctl; m.et = e->et; m.BS = c.max_trees; m.gamma_f32 = (float)c.gamma;
     m.head_dim = azg_head_dim(e);
     m.qdigits = e->qdigits; m.qfl = e->qfl; m.qfl_count = e->qfl_count;
     m.stats = e->stats;
+    {
+        const char* g = getenv("AZG_STAGGER_GROUPS");
+        const char* ns = getenv("AZG_STAGGER_NS");
+        m.stagger_groups = g ? atoi(g) : 1;
+        m.stagger_ns = ns ? atoi(ns) : 0;
+    }
     return m;
 }
 
@@ -506,7 +512,7 @@ static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const
     for (int lo = 0; lo < p.B; lo += chunk) {
         const int hi = std::min(p.B, lo + chunk);
         const int grid = std::max(1, std::min((hi - lo + 127) / 128, e->sm_count));
-        cudaError_t ce = launch_ex(e, k_qmlp2<S, ACT, NL, true>, grid, Q2_FUSED_THREADS, e->qmlp_smem, st, m, p, N, lo, hi);
+        cudaError_t ce = launch_ex(e, k_qmlp2<S, ACT, NL, true>, grid, Q2_THREADS, e->qmlp_smem, st, m, p, N, lo, hi);
         ++*launches;
         if (ce != cudaSuccess) return ce;
     }
@@ -806,6 +812,30 @@ extern "C" int azg_search_host(azg_engine* e, int32_t B, const double* h_root_st
     return rc;
 }
 
+// host copies of the tree-interleaved tables, back in per-tree order: ctl[t], et[t * 16 + j]
+static cudaError_t fetch_ctl(const azg_engine* e, int B, std::vector<CCtl>& out) {
+    const size_t BS = e->cfg.max_trees;
+    std::vector<uint4> plane(B);
+    out.resize(B);
+    for (int k = 0; k < 4; ++k) {
+        cudaError_t ce = cudaMemcpy(plane.data(), e->ctl + k * BS, (size_t)B * sizeof(uint4), cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) return ce;
+        for (int t = 0; t < B; ++t) reinterpret_cast<uint4*>(&out[t])[k] = plane[t];
+    }
+    return cudaSuccess;
+}
+static cudaError_t fetch_et(const azg_engine* e, int B, std::vector<CHot>& out) {
+    const size_t BS = e->cfg.max_trees;
+    std::vector<CHot> plane(B);
+    out.resize((size_t)B * CROOT_MAX_KIDS);
+    for (int j = 0; j < CROOT_MAX_KIDS; ++j) {
+        cudaError_t ce = cudaMemcpy(plane.data(), e->et + j * BS, (size_t)B * sizeof(CHot), cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) return ce;
+        for (int t = 0; t < B; ++t) out[(size_t)t * CROOT_MAX_KIDS + j] = plane[t];
+    }
+    return cudaSuccess;
+}
+
 extern "C" int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]) {
     if (!e || !out) return fail(AZG_EINVAL, "null argument");
     if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
@@ -820,8 +850,8 @@ extern "C" int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]) {
     if (e->cfg.variant == AZG_DISCRETE) {
         CK(cudaMemcpy(dr.data(), e->draws, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost));
     } else {
-        std::vector<CCtl> cc(B);
-        CK(cudaMemcpy(cc.data(), e->ctl, (size_t)B * sizeof(CCtl), cudaMemcpyDeviceToHost));
+        std::vector<CCtl> cc;
+        CK(fetch_ctl(e, B, cc));
         for (int t = 0; t < B; ++t) { dr[t] = cc[t].draws; pw[t] = cc[t].pw; }
     }
     for (int k = 0; k < 8; ++k) out[k] = 0;
@@ -942,12 +972,12 @@ extern "C" int azg_dump_tree_continuous(azg_engine* e, int32_t B, const azg_dump
     CK(cudaDeviceSynchronize());
     const size_t R = e->R, K3 = e->K3, HS = e->HS;
     std::vector<CRow> rows((size_t)B * R);
-    std::vector<CHot> et((size_t)B * CROOT_MAX_KIDS);
-    std::vector<CCtl> ctl(B);
+    std::vector<CHot> et;
+    std::vector<CCtl> ctl;
     std::vector<float> hd((size_t)B * R * HS);
     CK(cudaMemcpy(rows.data(), e->crows, rows.size() * sizeof(CRow), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(et.data(), e->et, et.size() * sizeof(CHot), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(ctl.data(), e->ctl, ctl.size() * sizeof(CCtl), cudaMemcpyDeviceToHost));
+    CK(fetch_et(e, B, et));
+    CK(fetch_ctl(e, B, ctl));
     CK(cudaMemcpy(hd.data(), e->chead, hd.size() * sizeof(float), cudaMemcpyDeviceToHost));
     std::vector<int32_t> par(R);
     std::vector<const CHot*> hot(R);

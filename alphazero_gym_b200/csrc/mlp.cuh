@@ -40,8 +40,9 @@ struct MlpParams {
     CRow* crows;
     float* chead;
     uint32_t* evals;     // per-tree evaluation counter
-    CCtl* ctl;           // continuous: leaf word; ctl[t].leafR += gamma_f32 * V  (first backup step, mcts.py:260-263)
-    CHot* et;            // continuous: root edge table (V of a root child is written there)
+    uint4* ctl;          // continuous: control-block chunk planes [4][BS] (common.cuh): leaf word; leafR += gamma_f32 * V (mcts.py:260-263)
+    CHot* et;            // continuous: root edge table [16][BS] (V of a root child is written there)
+    int32_t BS;          // plane stride of the tree-interleaved tables (max_trees)
     float gamma_f32;
     float* outV;
     float* outHead;
@@ -50,10 +51,11 @@ struct MlpParams {
     const int8_t* qdigits;
     const float* qfl;
     int32_t qfl_count;  // floats in qfl (multiple of 4)
-    // whole-search kernel: cycle accounting, summed over CTAs (azg_fused_stats): [0] kernel cycles, [1] epilogue warp 0 waiting
-    // for the next network inputs of a tile (xready: tree latency NOT hidden), [2] tree warp 0 of slot 0 waiting for an
-    // evaluation (hfull: slack), [3] the same warp inside finish + backup + select + expansion, [4] CTAs
+    // whole-search kernel: cycle accounting, summed over CTAs (azg_fused_stats, include/azg.h)
     unsigned long long* stats;
+    // whole-search kernel: CTA b starts (b % stagger_groups) * stagger_ns late, so that the tree phases of the groups (HBM-bound
+    // random access) do not fall on top of each other while their evaluations (no HBM traffic) do not care
+    int32_t stagger_groups, stagger_ns;
 };
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP / SYNCS) --------------
@@ -196,9 +198,9 @@ __device__ __forceinline__ void mlp_finish_row(const MlpParams& p, int gr, int l
             d->V = V;
             *reinterpret_cast<float2*>(d->prior) = make_float2(post[0], post[1]);
         } else {
-            if (leafw & LEAF_ROOTCHILD) p.et[(size_t)gr * CROOT_MAX_KIDS + ((leafw >> LEAF_J_SHIFT) & 0xFF)].V = V;
+            if (leafw & LEAF_ROOTCHILD) p.et[(size_t)((leafw >> LEAF_J_SHIFT) & 0xFF) * p.BS + gr].V = V;
             else p.crows[ri].V = V;
-            p.ctl[gr].leafR = lr + (double)__fmul_rn(p.gamma_f32, V);
+            reinterpret_cast<double*>(p.ctl + (size_t)p.BS + gr)[1] = lr + (double)__fmul_rn(p.gamma_f32, V);  // CCtl::leafR = chunk 1, bytes 8..15
             float* h = p.chead + ri * p.HS;  // HS is a multiple of 4 floats: vector stores
             for (int i = 0; i < npost; i += 4)
                 *reinterpret_cast<float4*>(h + i) = make_float4(post[i], i + 1 < npost ? post[i + 1] : 0.0f, i + 2 < npost ? post[i + 2] : 0.0f,
@@ -287,8 +289,7 @@ __device__ __forceinline__ void mlp_unit(const MlpParams& p, const float* w, flo
     double lr = 0.0;
     if (need && p.mode == 0) {
         if (p.variant == 1) {  // continuous: leaf word and leafR share the first 32 B of the control block
-            const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
-            const uint4 c0 = cp[0], c1 = cp[1];
+            const uint4 c0 = p.ctl[gr], c1 = p.ctl[(size_t)p.BS + gr];
             leafw = (int)c0.z;
             lr = __hiloint2double((int)c1.w, (int)c1.z);
         } else {

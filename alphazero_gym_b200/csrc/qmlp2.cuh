@@ -28,14 +28,8 @@
 
 #define Q2_EPI_THREADS 512
 #define Q2_THREADS 768                // 16 epilogue warps + the MMA warpgroup + the post-processing warpgroup (registers rebalanced with setmaxnreg)
-#define Q2_FUSED_THREADS 896          // whole-search kernel: 16 epilogue warps + the MMA warpgroup + one tree warpgroup per tile slot
-#ifndef Q2F_EPI_REGS
-#define Q2F_EPI_REGS 96               // whole-search kernel: 512 x 96 + 128 x 24 + 256 x 48 = 896 x 72, the CTA's register pool at launch
-#define Q2F_TREE_REGS 48
-#endif
-#define Q2_STR2(x) #x
-#define Q2_STR(x) Q2_STR2(x)
 #define Q2_MAX_TILES 16               // whole-search kernel: tiles per CTA and launch (engine.cu cuts larger batches into chunks)
+#define Q2_BAR_PHASE 6                // named barrier of the whole-search kernel: 16 epilogue warps + the post-processing warpgroup
 #define Q2_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24))  // s8 x s8 -> s32, K-major, N = 64, M = 128
 #define Q2_ACC_COLS 192               // accumulator window of a tile: PA | PB | PC, 64 columns each
 #define Q2_SCRATCH_COL 384            // head partial sums of tile T: columns 384 + 64 T + 16 cq + c
@@ -214,21 +208,21 @@ __device__ __forceinline__ void q2_finish_tile(const MlpParams& p, uint32_t tb, 
 // FUSED = false: one leaf evaluation of p.n rows (one launch per simulation, engine.cu enqueue_search).
 // FUSED = true: the WHOLE SEARCH of the continuous tree for the trees [chunk_begin, chunk_end) in one persistent launch.
 //   Trees never interact, so nothing needs a grid-wide barrier between simulations: a CTA owns its trees for the whole search
-//   and runs n_sims + 1 evaluations of each of its tiles back to back.  The post-processing warpgroup becomes one TREE
-//   warpgroup per tile slot: thread r finishes row r of the tile (head sums, policy post-processing, scatter) and goes straight
-//   on to that tree's backup + select + expansion for the next simulation (c_step, tree_continuous.cuh: the body of
-//   k_step_continuous), writes the next network input and signals xready[tile].  While the trees of one tile pair walk their
-//   dependent loads (HBM/L2 latency bound, ~20 % of the issue slots of an SM), the epilogue warps evaluate the other pair, so the
-//   tree step costs no time of its own, the evaluation pipeline never drains between simulations, and the weights are staged once
-//   per search instead of once per simulation.  Every table of a tree is read and written by ONE thread for the whole search;
-//   the only cross-thread traffic is X (tree thread -> epilogue warps, release/acquire through xready) and the head partial sums
-//   (epilogue -> tree thread, through TMEM and hfull).
+//   and alternates two phases, n_sims + 1 times: (1) the evaluation of all its tiles, exactly as above; (2) a TREE PHASE in which
+//   the 16 epilogue warps run one thread per tree: backup of the finished simulation, descent + expansion of the next (c_step,
+//   tree_continuous.cuh -- the body of k_step_continuous), next network input into X.  Two 640-thread named barriers separate the
+//   phases (epilogue warps + post-processing warpgroup; the MMA warp only follows its mbarriers).  What this buys over one launch
+//   per kernel and simulation: weights, TMEM and barriers are set up once per search instead of once per simulation (~10 us of
+//   ramp per evaluation launch, tools/step_scaling.py), no launch gaps, and the 148 CTAs drift out of phase, so the tree phases
+//   of some SMs overlap the evaluations of others and the HBM traffic of the tree walk is spread over the whole simulation
+//   instead of arriving in one burst.  The first version (git history, profiles/README.md r1f) overlapped the two phases INSIDE
+//   an SM with two dedicated tree warpgroups; at 48 registers per tree thread and with both code paths fighting for the
+//   instruction cache it reached 80 us per simulation against 74 us for separate launches.
 template <int S, int ACT, int NL, bool FUSED>
-__global__ void __launch_bounds__(FUSED ? Q2_FUSED_THREADS : Q2_THREADS, 1)
+__global__ void __launch_bounds__(Q2_THREADS, 1)
 k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chunk_begin, const int chunk_end) {
     extern __shared__ __align__(1024) uint8_t qsm_raw[];
     __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2], hfull[2], hfree[2];
-    __shared__ __align__(8) uint64_t xready[FUSED ? Q2_MAX_TILES : 1];
     __shared__ uint32_t tmem_base_s;
     // round up to 1024 B with an OFFSET on the shared pointer: a round trip through uintptr_t loses the address space and every
     // access below becomes a generic LD/ST (long-scoreboard latency) instead of LDS/STS
@@ -264,8 +258,6 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
             mbar_init(&hfull[T], Q2_EPI_THREADS);
             mbar_init(&hfree[T], 128);
         }
-        if (FUSED)
-            for (int t = 0; t < Q2_MAX_TILES; ++t) mbar_init(&xready[t], 128);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
@@ -291,70 +283,16 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
     }
     mbar_wait(&wbar, 0);
 
-    if (FUSED && warp >= 20) {
-        // ---- tree warpgroup of tile slot w: finishes the evaluated rows of its tiles and advances their trees
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 " Q2_STR(Q2F_TREE_REGS) ";");
-        const int w = (warp - 20) >> 2, lg = warp & 3, r = lg * 32 + lane;
-        const float* bh = fl + S * 128 + 128 + NL * 2 * 128 + 128 * p.PO_PAD;
-        uint32_t hph = 0, nev = 0;
-        int ev_row = 0;
-        long long cyc_wait = 0, cyc_work = 0;
-        const Tabs tabs = {s_pw, s_rcp, s_sq, FUSED_TAB};
-#pragma unroll 1
-        for (int t = w; t < ntiles; t += 2) {  // MCTSContinuous.initialize_search for every tree of the tile
-            const int row0 = row_begin + t * th;
-            const int nv = max(0, min(th, row_end - row0));
-            if (r < nv) c_init(tp, row0 + r);
-            mbar_arrive(&xready[t]);
-        }
-#pragma unroll 1
-        for (int s = 0; s < n_evals; ++s) {
-#pragma unroll 1
-            for (int t = w; t < ntiles; t += 2) {
-                const int row0 = row_begin + t * th;
-                const int nv = max(0, min(th, row_end - row0));
-                const int gr = row0 + r;
-                const bool valid = r < nv;
-                bool need = valid;
-                int leafw = 0;
-                double lr = 0.0;
-                if (valid) {
-                    const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
-                    const uint4 c0 = cp[0], c1 = cp[1], c2 = cp[2];
-                    leafw = (int)c0.z;
-                    lr = __hiloint2double((int)c1.w, (int)c1.z);
-                    need = (leafw & LEAF_EVAL) != 0;
-                    c_prefetch(tp, gr, c0, c2);  // HBM -> L2 while the tile is being evaluated
-                }
-                const long long c0 = clock64();
-                mbar_wait(&hfull[w], hph);
-                hph ^= 1u;
-                const long long c1 = clock64();
-                tc_fence_after();
-                if (lg * 32 < nv) q2_finish_tile(p, tb, bh, lg, w, need, gr, leafw, lr, hfree, nev, ev_row);
-                else mbar_arrive(&hfree[w]);
-                if (valid) {
-                    if (s == 0) c_root_insert(tp, gr);         // the add_pw_action(root) before the loop (mcts.py:673)
-                    c_step(tp, tabs, gr, s > 0, s + 1 < n_evals);  // backup of simulation s, descent + expansion of simulation s + 1
-                }
-                __syncwarp();
-                if (s + 1 < n_evals) mbar_arrive(&xready[t]);  // releases X[gr] to the epilogue warps
-                cyc_wait += c1 - c0;
-                cyc_work += clock64() - c1;
-            }
-        }
-        if (nev) p.evals[ev_row] += nev;
-        if (tid == 640 && p.stats) {
-            atomicAdd(p.stats + 2, (unsigned long long)cyc_wait);
-            atomicAdd(p.stats + 3, (unsigned long long)cyc_work);
-        }
-    } else if (warp >= 20) {
+    if (warp >= 20) {
         // ---- post-processing warpgroup: warp 20 + lg finishes the rows of row group lg, tile after tile
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         const int lg = warp & 3, r = lg * 32 + lane;
         const float* bh = fl + S * 128 + 128 + NL * 2 * 128 + 128 * p.PO_PAD;
         uint32_t hph = 0, nev = 0;
         int ev_row = 0;
+        if (FUSED) group_sync(Q2_BAR_PHASE, 640);  // the roots are initialised (c_init)
+#pragma unroll 1
+        for (int s = 0; s < n_evals; ++s) {
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
             const int T = t & 1;
@@ -366,8 +304,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
             double lr = 0.0;
             if (need && p.mode == 0) {  // loaded before the wait: the latency hides under the tile's evaluation
                 if (p.variant == 1) {
-                    const uint4* cp = reinterpret_cast<const uint4*>(p.ctl + gr);
-                    const uint4 c0 = cp[0], c1 = cp[1];
+                    const uint4 c0 = p.ctl[gr], c1 = p.ctl[(size_t)p.BS + gr];
                     leafw = (int)c0.z;
                     lr = __hiloint2double((int)c1.w, (int)c1.z);
                 } else {
@@ -380,6 +317,11 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
             tc_fence_after();
             if (lg * 32 < nv) q2_finish_tile(p, tb, bh, lg, T, need, gr, leafw, lr, hfree, nev, ev_row);
             else mbar_arrive(&hfree[T]);
+        }
+        if (FUSED) {
+            group_sync(Q2_BAR_PHASE, 640);  // every row of this evaluation is finished: the tree phase may start
+            group_sync(Q2_BAR_PHASE, 640);  // the tree phase is over: leaf words and X of the next simulation are in place
+        }
         }
         if (nev && p.mode == 0) p.evals[ev_row] += nev;  // only the total over trees is reported (azg_get_counters)
     } else if (warp >= 16) {
@@ -422,8 +364,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         }
     } else {
         // ---- epilogue warps
-        if (FUSED) asm volatile("setmaxnreg.inc.sync.aligned.u32 " Q2_STR(Q2F_EPI_REGS) ";");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");       // 512 x 104 + 128 x 24 + 128 x 40 = 768 x 80
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 512 x 104 + 128 x 24 + 128 x 40 = 768 x 80, the CTA's pool at launch
         Q2Ctx c;
         c.W0 = fl;
         c.b0 = fl + S * 128;
@@ -436,12 +377,21 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         c.tb = tb;
         c.lg = warp & 3; c.cq = warp >> 2;
         c.r = c.lg * 32 + lane;
-        long long cyc_x = 0;
+        long long cyc_tree = 0, cyc_sync = 0;
         const long long cyc_begin = clock64();
+        const Tabs tabs = {s_pw, s_rcp, s_sq, FUSED_TAB};
+        if (FUSED) {  // MCTSContinuous.initialize_search for every tree of the CTA
+            if (p.stagger_groups > 1) {
+                const long long until = cyc_begin + (long long)(blockIdx.x % p.stagger_groups) * p.stagger_ns * 2;  // ~2 cycles per ns
+                while (clock64() < until) __nanosleep(1000);
+            }
+            for (int i = tid; i < nrows; i += Q2_EPI_THREADS) c_init(tp, row_begin + i);
+            group_sync(Q2_BAR_PHASE, 640);
+        }
         uint32_t fullph = 0;  // bit T: parity of the next wait on full[T]
         uint32_t hfph = 0;    // bit T: parity of the next wait on hfree[T]
 #pragma unroll 1
-        for (int s = 0; s < n_evals; ++s)
+        for (int s = 0; s < n_evals; ++s) {
 #pragma unroll 1
         for (int t0 = 0; t0 < ntiles; t0 += 2) {
             const int nt = min(2, ntiles - t0);
@@ -450,11 +400,6 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
             for (int T = 0; T < nt; ++T) {
                 const int row0 = row_begin + (t0 + T) * th;
                 const int nv = max(0, min(th, row_end - row0));
-                if (FUSED) {  // the tile's trees have written their next network inputs
-                    const long long c0 = clock64();
-                    mbar_wait(&xready[t0 + T], (uint32_t)s & 1u);
-                    cyc_x += clock64() - c0;
-                }
                 const float cx = q2_layer0<S, ACT>(c, p, T, c.lg * 32 < nv, row0 + c.r, c.r < nv);
                 if (T == 0) cx0 = cx; else cx1 = cx;
             }
@@ -526,9 +471,26 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
                 }
             }
         }
+        if (FUSED) {
+            // ---- tree phase: one thread per tree of the CTA
+            const long long c0 = clock64();
+            group_sync(Q2_BAR_PHASE, 640);  // the post-processing warps have finished every row of this evaluation
+            const long long c1 = clock64();
+#pragma unroll 1
+            for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
+                const int gr = row_begin + i;
+                if (s == 0) c_root_insert(tp, gr);                // the add_pw_action(root) before the loop (mcts.py:673)
+                c_step(tp, tabs, gr, s > 0, s + 1 < n_evals);     // backup of simulation s, descent + expansion of simulation s + 1
+            }
+            group_sync(Q2_BAR_PHASE, 640);
+            cyc_sync += c1 - c0;
+            cyc_tree += clock64() - c1;
+        }
+        }
         if (FUSED && tid == 0 && p.stats) {
             atomicAdd(p.stats + 0, (unsigned long long)(clock64() - cyc_begin));
-            atomicAdd(p.stats + 1, (unsigned long long)cyc_x);
+            atomicAdd(p.stats + 1, (unsigned long long)cyc_tree);
+            atomicAdd(p.stats + 2, (unsigned long long)cyc_sync);
             atomicAdd(p.stats + 4, 1ull);
         }
     }

@@ -54,17 +54,18 @@ __device__ __forceinline__ void store_sec1_new(CRow* p, double th, double thdot)
     q[3] = make_uint4((uint32_t)__double2loint(th), (uint32_t)__double2hiint(th), (uint32_t)__double2loint(thdot),
                       (uint32_t)__double2hiint(thdot));
 }
-__device__ __forceinline__ CCtl load_ctl(const CCtl* p) {
+// control block of tree t: four 16-byte chunks in four tree-interleaved planes (common.cuh)
+__device__ __forceinline__ CCtl load_ctl(const uint4* ctl, int BS, int t) {
     CCtl c;
-    const uint4* s = reinterpret_cast<const uint4*>(p);
     uint4* d = reinterpret_cast<uint4*>(&c);
-    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = ctl[(size_t)k * BS + t];
     return c;
 }
-__device__ __forceinline__ void store_ctl(CCtl* p, const CCtl& c) {
+__device__ __forceinline__ void store_ctl(uint4* ctl, int BS, int t, const CCtl& c) {
     const uint4* s = reinterpret_cast<const uint4*>(&c);
-    uint4* d = reinterpret_cast<uint4*>(p);
-    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ctl[(size_t)k * BS + t] = s[k];
 }
 // byte j of a 16-byte list held in four registers, without dynamic register indexing
 __device__ __forceinline__ int list_byte(const uint32_t w[4], int j) {
@@ -136,7 +137,7 @@ __device__ __forceinline__ void c_init(const TreeParams& p, int t) {
     memset(&c, 0, sizeof c);
     c.n_rows = 1;
     c.leaf = 0 | LEAF_EVAL;
-    store_ctl(p.ctl + t, c);
+    store_ctl(p.ctl, p.BS, t, c);
     for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
 }
 __global__ void k_init_continuous(const TreeParams p) {
@@ -147,9 +148,9 @@ __global__ void k_init_continuous(const TreeParams p) {
 // the add_pw_action(root) that precedes the rollout loop (mcts.py:673); runs after the root evaluation
 __device__ __forceinline__ void c_root_insert(const TreeParams& p, int t) {
     CRow* rows = p.crows + (size_t)t * p.R;
-    CCtl c = load_ctl(p.ctl + t);
+    CCtl c = load_ctl(p.ctl, p.BS, t);
     const float a = new_action(p, t, 0, 1, 0);
-    store_hot(p.et + (size_t)t * CROOT_MAX_KIDS, fresh_hot(0.0, 0.0f, a, 0));
+    store_hot(p.et + t, fresh_hot(0.0, 0.0f, a, 0));  // root child 0
     store_hot(rows + 1, fresh_hot(0.0, 0.0f, a, 0));  // unused mirror of the edge-table entry (keeps the row defined)
     store_sec1_new(rows + 1, 0.0, 0.0);
     c.root_kids[0] = 1;
@@ -158,7 +159,7 @@ __device__ __forceinline__ void c_root_insert(const TreeParams& p, int t) {
     c.pw = 1;
     c.root_V = rows[0].V;  // written by the root evaluation
     c.root_nn = 0;
-    store_ctl(p.ctl + t, c);
+    store_ctl(p.ctl, p.BS, t, c);
 }
 __global__ void k_root_insert_continuous(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,9 +177,8 @@ __global__ void k_root_insert_continuous(const TreeParams p) {
 // registers) and there is one instance of it for root and inner nodes: the first version unrolled 16 children x 2 call sites
 // x two inlined IEEE divisions into 5000 SASS instructions, which the whole-search kernel (qmlp2.cuh) paid for in instruction
 // fetch on the evaluation warps.
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ const CHot* child_hot(const CHot* et, const CRow* rows, const uint32_t kw[4], bool is_root, int j) {
-    return is_root ? et + j : reinterpret_cast<const CHot*>(rows + list_byte(kw, j));
+__device__ __forceinline__ const CHot* child_hot(const CHot* et, int BS, const CRow* rows, const uint32_t kw[4], bool is_root, int j) {
+    return is_root ? et + (size_t)j * BS : reinterpret_cast<const CHot*>(rows + list_byte(kw, j));  // et = &table[0][t]
 }
 __device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, int64_t tree, int nk, uint32_t cur_nn, float cur_V, int& draws,
                                           bool& nan, const CHot* et, const CRow* rows, const uint32_t kw[4], bool is_root) {
@@ -191,12 +191,9 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, i
         int n[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const CHot* h = child_hot(et, rows, kw, is_root, w0 + i < nk ? w0 + i : w0);
+            const CHot* h = child_hot(et, p.BS, rows, kw, is_root, w0 + i < nk ? w0 + i : w0);
             W[i] = h->W;
             n[i] = h->n_e;
-            // the second sector of an inner node's child (its child list + env state) is the other half of the same 64 B DRAM
-            // burst: requested now, it is there when the descent enters the winner
-            if (!is_root) prefetch_l1(reinterpret_cast<const char*>(h) + 32);
         }
         const int m = min(4, nk - w0);
 #pragma unroll 1
@@ -223,47 +220,25 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, i
     return nw > 0 ? (int)__fns(win, 0, pick + 1) : 0;
 }
 
-// Whole-search kernel: while a tree thread waits for its tile's evaluation it pulls the lines its next step is known to touch
-// from HBM into L2 (the control block's path rows for the backup, the root edge table for the first UCT scan).
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void c_prefetch(const TreeParams& p, int t, const uint4 c0, const uint4 c2) {
-    const CRow* rows = p.crows + (size_t)t * p.R;
-    const CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
-    const int depth = (int)((c0.x >> 8) & 0xFFu), root_nk = (int)((c0.x >> 16) & 0xFFu);
-    for (int j = 0; j < root_nk; j += 4) prefetch_l2(et + j);  // 128 B lines
-    const uint32_t pw[4] = {c2.x, c2.y, c2.z, c2.w};
-    for (int i = 1; i < min(depth, 16); ++i) prefetch_l2(rows + list_byte(pw, i));
-}
-
 // one simulation step of tree t: backup of the previous simulation (BACKUP), then descent + expansion of the next (SELECT).
 // Shared by k_step_continuous (one launch per simulation) and the whole-search kernel k_search_fused (fused.cuh).
 __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int t, const bool BACKUP, const bool SELECT) {
     CRow* rows = p.crows + (size_t)t * p.R;
-    CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
+    CHot* et = p.et + t;  // root child j: et[j * BS]
     uint8_t* path_ovf = p.path + (size_t)t * p.R;
     // per-tree counters: read here, written at the end (a read-modify-write at the end exposed the load latency)
     uint32_t ctr_levels = 0, ctr_scanned = 0;
     if (SELECT) { ctr_levels = p.ctr[t]; ctr_scanned = p.ctr[(size_t)p.B + t]; }
-    CCtl c = load_ctl(p.ctl + t);
+    CCtl c = load_ctl(p.ctl, p.BS, t);
     uint32_t pathw[4];
     memcpy(pathw, c.path, 16);
-    // The step is a chain of dependent loads (profiles/r1e: 13 long-scoreboard stall cycles per issued instruction), so every
-    // line whose address is known now is requested now: the rows of the recorded path (backup), the root edge table (backup
-    // of the root edge + first UCT scan) and the root's policy head if the root is about to be widened.
-    {
-        const int d = BACKUP ? (int)c.depth : 0;
-        for (int i = 1; i < min(d, 16); ++i) prefetch_l1(rows + list_byte(pathw, i));
-        for (int j = 0; j < (int)c.root_nk; j += 4) prefetch_l1(et + j);
-        if (SELECT && tb.pw[c.root_nn + (d > 0 ? 1 : 0)] - (int)c.root_nk > 0) prefetch_l1(p.chead + (size_t)t * p.R * p.HS);
-    }
-
     if (BACKUP) {
         // backprop (mcts.py:241-267) along the recorded path.  leafR already holds r_leaf + gamma*V_leaf
         // (the f32 product of NEP 50, added by the evaluation kernel's epilogue).
         const int d = c.depth;
         double Rv = c.leafR;
         for (int i = d - 1; i >= 0; --i) {
-            void* hp = i == 0 ? (void*)(et + c.j0) : (void*)(rows + (i < 16 ? list_byte(pathw, i) : (int)path_ovf[i]));
+            void* hp = i == 0 ? (void*)(et + (size_t)c.j0 * p.BS) : (void*)(rows + (i < 16 ? list_byte(pathw, i) : (int)path_ovf[i]));
             const CHot h = load_hot(hp);
             if (i != d - 1) Rv = h.r + p.gamma * Rv;
             reinterpret_cast<CHot*>(hp)->W = h.W + Rv;  // Action.update (states.py:97-112)
@@ -290,10 +265,9 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
             if (tb.pw[cur_nn] - nk > 0) { kind = KIND_INSERT; break; }  // states.py:252-275
             jsel = uct_select(p, tb, tree, nk, cur_nn, cur_V, draws, nan, et, rows, kw, cur == 0);
             sel = list_byte(kw, jsel);
-            const CHot sh = load_hot(child_hot(et, rows, kw, cur == 0, jsel));  // the line was gathered a moment ago
+            const CHot sh = load_hot(child_hot(et, p.BS, rows, kw, cur == 0, jsel));  // the line was gathered a moment ago
             // requested together with sh (one round trip instead of two); used only if the descent enters the node
             const CSec1 s1 = load_sec1(rows + sel);
-            prefetch_l1(p.chead + ((size_t)t * p.R + sel) * p.HS);  // the node's cached policy head, read if the node is widened
             scanned += nk;
             if (depth == 0) c.j0 = (uint8_t)jsel;
             if (depth < 16) set_list_byte(pathw, depth, sel); else path_ovf[depth] = (uint8_t)sel;
@@ -343,7 +317,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
             const uint32_t fl = CROW_EXPANDED | (term ? CROW_TERMINAL : 0u);
             float V = 0.0f;
             if (p.use_tape && !term) V = p.tapeV[(size_t)t * p.R + sel];
-            void* hp = parent_is_root ? (void*)(et + jsel) : (void*)(rows + sel);
+            void* hp = parent_is_root ? (void*)(et + (size_t)jsel * p.BS) : (void*)(rows + sel);
             if (kind == KIND_INSERT) {
                 store_hot(hp, fresh_hot(r, V, sel_action, fl));
                 if (parent_is_root) store_hot(rows + sel, fresh_hot(r, V, sel_action, fl));  // defined but unused mirror
@@ -373,7 +347,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
         memcpy(c.root_kids, rootk, 16);
     }
     memcpy(c.path, pathw, 16);
-    store_ctl(p.ctl + t, c);
+    store_ctl(p.ctl, p.BS, t, c);
 }
 template <bool BACKUP, bool SELECT>
 __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
@@ -404,14 +378,14 @@ __global__ void k_results_continuous(const TreeParams p, int cmax, float* action
                                      int32_t* nchild) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.B) return;
-    const CHot* et = p.et + (size_t)t * CROOT_MAX_KIDS;
-    const CCtl c = load_ctl(p.ctl + t);
+    const CHot* et = p.et + t;
+    const CCtl c = load_ctl(p.ctl, p.BS, t);
     const float Vroot = c.root_V;
     const int nk = min((int)c.root_nk, cmax);
     double q[CROOT_MAX_KIDS];
     int32_t cn[CROOT_MAX_KIDS];
     for (int j = 0; j < nk; ++j) {
-        const CHot h = load_hot(et + j);
+        const CHot h = load_hot(et + (size_t)j * p.BS);
         q[j] = h.n_e > 0 ? h.W / (double)h.n_e : (double)Vroot;
         cn[j] = h.n_e;
         actions[(size_t)t * cmax + j] = h.action;

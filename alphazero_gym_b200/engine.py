@@ -241,8 +241,8 @@ class SearchEngine:
         arr = (C.c_int64 * 8)()
         check(self._lib.azg_fused_stats(self._h, C.byref(arr)))
         tot = max(1, int(arr[0]))
-        return {"ctas": int(arr[4]), "kernel_cycles_per_cta": tot / max(1, int(arr[4])), "eval_waits_for_trees": arr[1] / tot,
-                "trees_wait_for_eval": arr[2] / tot, "tree_work": arr[3] / tot}
+        return {"ctas": int(arr[4]), "kernel_cycles_per_cta": tot / max(1, int(arr[4])), "tree_phase": arr[1] / tot,
+                "wait_for_post_processing": arr[2] / tot}
 
     # ---- standalone kernels (known-answer tests) ---------------------------------------------------------
     def mlp_forward(self, x: np.ndarray):

@@ -197,10 +197,10 @@ int azg_dump_tree_continuous(azg_engine* e, int32_t B, const azg_dump_continuous
  * ended on a terminal node, [7] kernels launched (or graph nodes replayed). */
 int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]);
 
-/* Cycle accounting of the whole-search kernel (AZG_FLAG_FUSED) since the last call, summed over CTAs, then reset:
- * out[0] kernel cycles, out[1] cycles the evaluation warps waited for the trees of a tile (tree latency that was NOT hidden),
- * out[2] cycles a tree warp waited for an evaluation (slack), out[3] cycles that warp spent in finish + backup + select +
- * expansion, out[4] CTAs counted.  Synchronises the device. */
+/* Cycle accounting of the whole-search kernel (AZG_FLAG_FUSED) since the last call, summed over CTAs, then reset (measured on
+ * thread 0 of each CTA): out[0] kernel cycles, out[1] cycles in the tree phases (backup + select + expansion of every tree of the
+ * CTA, up to the closing barrier), out[2] cycles waiting for the post-processing warps before a tree phase, out[4] CTAs counted.
+ * Synchronises the device. */
 int azg_fused_stats(azg_engine* e, int64_t out[8]);
 
 /* Measurement hook: runs one search with direct launches, a CUDA-event pair around every kernel, and
