@@ -12,6 +12,7 @@
 //   * COLD structure-of-arrays side tables that select/backup never touch: CartPole env state, cached policy head.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #define AZG_MAX_K 8
@@ -39,12 +40,13 @@ struct __align__(16) CRow {  // ActionContinuous + the NodeContinuous it leads t
     // sector 0 ("hot" sector, struct CHot) -- read for every child scanned by UCT and rewritten by backup.
     // For children of the ROOT this sector is not used: their hot sectors live contiguously in the root edge
     // table (TreeParams::et), because the root is scanned in every simulation and has up to 16 children.
+    // first 16 bytes = everything the UCT scan reads (one LDG.128 per child) and everything backup writes (one STG.128)
     double W;                // Action.W
+    int32_t n_e;             // Action.n
+    uint32_t nn_flags;       // child Node.n in bits 0..23 | CROW_EXPANDED | CROW_TERMINAL
     double r;                // child Node.r (already / PENDULUM_R_SCALE)
     float V;                 // child Node.V
     float action;            // Action.action
-    int32_t n_e;             // Action.n
-    uint32_t nn_flags;       // child Node.n in bits 0..23 | CROW_EXPANDED | CROW_TERMINAL
     // sector 1 -- the child node's own child_actions list (insertion order) and its hidden env state; read
     // only when the descent enters this node, appended to by progressive widening
     uint8_t kids[15];        // row indices
@@ -60,11 +62,13 @@ static_assert(sizeof(CRow) == 64, "continuous row must be two 32 B sectors (one 
 #define CROW_TERMINAL 0x02000000u
 
 struct __align__(16) CHot {  // sector 0 of a CRow / one entry of the root edge table
-    double W, r;
-    float V, action;
+    double W;
     int32_t n_e;
     uint32_t nn_flags;
+    double r;
+    float V, action;
 };
+static_assert(offsetof(CHot, n_e) == 8 && offsetof(CHot, r) == 16 && offsetof(CRow, r) == 16 && offsetof(CRow, kids) == 32, "hot sector layout");
 static_assert(sizeof(CHot) == 32, "hot sector");
 
 struct __align__(16) CCtl {  // per-tree control block: everything a simulation needs besides rows, in ONE 64 B line

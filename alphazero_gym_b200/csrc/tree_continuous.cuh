@@ -115,9 +115,18 @@ __device__ __forceinline__ float sample_action(const TreeParams& p, const float*
 
 __device__ __forceinline__ float new_action(const TreeParams& p, int t, int node, int row, int j) {
     if (p.use_tape) return p.tapeA[(size_t)t * p.R + row];
+    // the node's cached policy head (mu[K], sigma[K], prob[K]; HS = 3K rounded up to 4 floats) in 16-byte loads issued before the noise
+    float head[3 * AZG_MAX_K];
+    const float4* hp = reinterpret_cast<const float4*>(p.chead + ((size_t)t * p.R + node) * p.HS);
+#pragma unroll
+    for (int i = 0; i < 3 * AZG_MAX_K / 4; ++i)
+        if (4 * i < p.HS) {
+            const float4 v = hp[i];
+            head[4 * i] = v.x; head[4 * i + 1] = v.y; head[4 * i + 2] = v.z; head[4 * i + 3] = v.w;
+        }
     float u, z[AZG_MAX_K];
     pw_noise(p, p.tree_id0 + t, j, u, z);
-    return sample_action(p, p.chead + ((size_t)t * p.R + node) * p.HS, u, z);
+    return sample_action(p, head, u, z);
 }
 
 __device__ __forceinline__ CHot fresh_hot(double r, float V, float action, uint32_t nn_flags) {
@@ -151,7 +160,6 @@ __device__ __forceinline__ void c_root_insert(const TreeParams& p, int t) {
     CCtl c = load_ctl(p.ctl, p.BS, t);
     const float a = new_action(p, t, 0, 1, 0);
     store_hot(p.et + t, fresh_hot(0.0, 0.0f, a, 0));  // root child 0
-    store_hot(rows + 1, fresh_hot(0.0, 0.0f, a, 0));  // unused mirror of the edge-table entry (keeps the row defined)
     store_sec1_new(rows + 1, 0.0, 0.0);
     c.root_kids[0] = 1;
     c.root_nk = 1;
@@ -191,9 +199,9 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, i
         int n[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const CHot* h = child_hot(et, p.BS, rows, kw, is_root, w0 + i < nk ? w0 + i : w0);
-            W[i] = h->W;
-            n[i] = h->n_e;
+            const uint4 q = *reinterpret_cast<const uint4*>(child_hot(et, p.BS, rows, kw, is_root, w0 + i < nk ? w0 + i : w0));
+            W[i] = __hiloint2double((int)q.y, (int)q.x);  // CHot::W
+            n[i] = (int)q.z;                              // CHot::n_e
         }
         const int m = min(4, nk - w0);
 #pragma unroll 1
@@ -241,8 +249,9 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
             void* hp = i == 0 ? (void*)(et + (size_t)c.j0 * p.BS) : (void*)(rows + (i < 16 ? list_byte(pathw, i) : (int)path_ovf[i]));
             const CHot h = load_hot(hp);
             if (i != d - 1) Rv = h.r + p.gamma * Rv;
-            reinterpret_cast<CHot*>(hp)->W = h.W + Rv;  // Action.update (states.py:97-112)
-            *reinterpret_cast<int2*>(&reinterpret_cast<CHot*>(hp)->n_e) = make_int2(h.n_e + 1, (int)(h.nn_flags + (i < d - 1 ? 1u : 0u)));
+            const double Wn = h.W + Rv;  // Action.update (states.py:97-112): W, n and the child node's n in one 16-byte store
+            *reinterpret_cast<uint4*>(hp) = make_uint4((uint32_t)__double2loint(Wn), (uint32_t)__double2hiint(Wn), (uint32_t)(h.n_e + 1),
+                                                       h.nn_flags + (i < d - 1 ? 1u : 0u));
         }
         if (d > 0) c.root_nn += 1;  // root.n
     }
@@ -299,8 +308,9 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
                 set_list_byte(rootk, nk, sel);
                 c.root_nk = (uint8_t)(nk + 1);
             } else {
-                rows[cur].kids[nk] = (uint8_t)sel;
-                rows[cur].nkids = (uint8_t)(nk + 1);
+                set_list_byte(kw, nk, sel);  // the node's child list + count (top byte) go back in one 16-byte store
+                kw[3] = (kw[3] & 0x00FFFFFFu) | ((uint32_t)(nk + 1) << 24);
+                reinterpret_cast<uint4*>(rows + cur)[2] = make_uint4(kw[0], kw[1], kw[2], kw[3]);
             }
             if (depth == 0) c.j0 = (uint8_t)jsel;
             if (depth < 16) set_list_byte(pathw, depth, sel); else path_ovf[depth] = (uint8_t)sel;
@@ -320,7 +330,6 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
             void* hp = parent_is_root ? (void*)(et + (size_t)jsel * p.BS) : (void*)(rows + sel);
             if (kind == KIND_INSERT) {
                 store_hot(hp, fresh_hot(r, V, sel_action, fl));
-                if (parent_is_root) store_hot(rows + sel, fresh_hot(r, V, sel_action, fl));  // defined but unused mirror
             } else {
                 CHot* h = reinterpret_cast<CHot*>(hp);
                 h->r = r; h->V = V; h->nn_flags = fl;
