@@ -247,7 +247,13 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
     const int nrows = row_end - row_begin;
     int ntiles = (nrows + 127) / 128;
     if (ntiles > 1) ntiles = (ntiles + 1) & ~1;
+#ifdef Q2_EQUAL_TILES
     const int th = (nrows + ntiles - 1) / ntiles;
+#else
+    // full tiles first, the remainder in the last one(s): epilogue work is spent per 32-row group, so 443 rows cost 14 row groups
+    // as 128 + 128 + 128 + 59 against 16 as four tiles of 111 (the warps of the empty row groups leave their issue slots to the others)
+    const int th = 128;
+#endif
 
     if (tid == 0) {
         mbar_init(&wbar, 1);

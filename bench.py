@@ -369,6 +369,44 @@ def main():
                  "algorithmic_bytes_per_sim": algorithmic_bytes(variant, pc) / max(1, pc["sims"]),
                  "share_of_step": tr["ms"] / (ev["ms"] + tr["ms"] + prof["setup"]["ms"])}
     dominant = roof_eval if ev["ms"] >= tr["ms"] else roof_tree
+    roof_all = {"evaluation": roof_eval, "tree_step": roof_tree}
+    if eng.cfg.is_fused():
+        # The search runs as ONE persistent kernel (AZG_FLAG_FUSED); the per-kernel numbers above are those of the same search as one
+        # launch per kernel and simulation (azg_profile_search always takes that path) and stay in roofline_all for comparison.
+        eng.fused_stats()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, args.steps)
+        f0.record()
+        for _ in range(reps):
+            eng.search(roots_d, N, tree_id0=tree_id0)
+        f1.record()
+        torch.cuda.synchronize()
+        k_ms = f0.elapsed_time(f1) / reps / max(1, counters["launches"])
+        st = eng.fused_stats()
+        fc = eng.counters()
+        flop = FLOP_PER_EVAL[variant] * fc["evals"] / max(1, counters["launches"])
+        tflops = flop / (k_ms * 1e-3) / 1e12
+        ev_ms, tree_ms = k_ms * (1.0 - st["tree_phase"]), k_ms * st["tree_phase"]
+        tbytes = algorithmic_bytes(variant, fc) / max(1, counters["launches"])
+        hh = 2 * 128 * 128 * 2
+        dominant = {
+            "kernel": "k_qmlp2<FUSED> (whole search in one persistent kernel: per simulation an evaluation phase on tcgen05 kind::i8 "
+                      "and a tree phase, backup + select + expansion, one thread per tree)",
+            "bound": "tensor", "achieved": tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tflops / bf16_peak,
+            "traffic": traffic.get("k_search"), "peak_source": peak_src + " dense bf16; int8 digits: 6 MMAs per algorithmic product",
+            "avg_launch_ms": k_ms, "launches": counters["launches"], "flop_per_launch": flop,
+            "tensor_tops_issued": 6 * hh * fc["evals"] / max(1, counters["launches"]) / (k_ms * 1e-3) / 1e12,
+            "frac_of_fp32_cuda_core_peak": tflops / fp32_peak, "share_of_step": 1.0,
+            "phases": {
+                "evaluation": {"share": 1.0 - st["tree_phase"], "ms_per_launch": ev_ms, "tflops_in_phase": flop / (ev_ms * 1e-3) / 1e12,
+                               "frac_of_tensor_peak_in_phase": flop / (ev_ms * 1e-3) / 1e12 / bf16_peak,
+                               "frac_of_fp32_cuda_core_peak_in_phase": flop / (ev_ms * 1e-3) / 1e12 / fp32_peak},
+                "tree": {"share": st["tree_phase"], "ms_per_launch": tree_ms, "algorithmic_bytes_per_launch": tbytes,
+                         "hbm_gbs_in_phase": tbytes / (tree_ms * 1e-3) / 1e9, "frac_of_hbm_peak_in_phase": tbytes / (tree_ms * 1e-3) / 1e9 / hbm_peak,
+                         "bound": "dependent-load latency chain + L1 tag lookups of per-thread scattered accesses (profiles/README.md r1f/r1g)"},
+                "source": "in-kernel cycle counters (azg_fused_stats)"},
+        }
+        roof_all = {"whole_search_kernel": dominant, "per_simulation_launches": {"evaluation": roof_eval, "tree_step": roof_tree}}
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
     cpu = None
@@ -392,7 +430,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 tree statistics + env dynamics / " + ("f32 network with exact int8-sliced tensor-core products" if args.eval == "q8" else "f32 network"),
             "data": "synthetic",
-            "config": {"workload": args.workload, "eval": args.eval, "env": "Pendulum-v0" if variant == "continuous" else "CartPole-v0",
+            "config": {"workload": args.workload, "eval": args.eval, "whole_search_kernel": bool(eng.cfg.is_fused()), "env": "Pendulum-v0" if variant == "continuous" else "CartPole-v0",
                        "trees_per_gpu": B, "global_trees": B * world, "n_rollouts": N, "parallelism": f"tree-sharded x{world}, no data-path collective",
                        "weights": "default init, torch.manual_seed(34)", "roots": "numpy default_rng(34)",
                        "l2": "node tables per GPU (%.0f MB) exceed the 126 MB L2; no explicit flush" % (eng.rows * B * (32 + 16 + 32) / 1e6)
@@ -405,7 +443,7 @@ def main():
                              "backend": "nccl" if world > 1 else "none (1 GPU)"}} if selfplay else {}),
             "clocks": clk,
             "roofline": dominant,
-            "roofline_all": {"evaluation": roof_eval, "tree_step": roof_tree},
+            "roofline_all": roof_all,
             "counters_per_sim": {k: pc[k] / max(1, pc["sims"]) for k in ("levels", "children_scanned", "pw_inserts", "evals")},
             "cpu_baseline": cpu,
         }
