@@ -231,6 +231,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries the one JSON line and nothing else: NCCL's own log (its version banner under NCCL_DEBUG=VERSION/INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
