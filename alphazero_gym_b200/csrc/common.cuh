@@ -123,6 +123,8 @@ struct TreeParams {
     int32_t* draws;   // selection RNG draw counter (stream 0)
     int32_t* leaf;    // LEAF_* word
     uint8_t* path;    // [B][R] continuous: path entries beyond the 16 held in CCtl
+    uint16_t* dpath;  // [B][R] discrete: the current simulation's path, (row << 1 | action) per level, root first (read by the backup)
+    int32_t* ddepth;  // [B]    discrete: its length
     uint32_t* ctr;    // [4][B]: levels, children scanned, terminal-leaf sims, evals
     float4* X;        // [B] network input of the leaf
     const double* root_state;
@@ -189,6 +191,37 @@ __device__ __forceinline__ u32x4 rng_block(uint64_t seed, int64_t tree, int stre
     c.z = (uint32_t)tree;
     c.w = (uint32_t)((uint64_t)tree >> 32) ^ ((uint32_t)stream << 24);
     return philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// four selection draws at once (.x of the blocks of draw indices idx0, idx0 + stride, ...): the four Philox chains are
+// independent, so they interleave in the pipeline and cost about the latency of one
+__device__ __forceinline__ void rng_select_u32x4(uint64_t seed, int64_t tree, int idx0, int stride, uint32_t out[4]) {
+    uint32_t cx[4], cy[4], cz[4], cw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int64_t idx = idx0 + q * stride;
+        cx[q] = (uint32_t)idx;
+        cy[q] = (uint32_t)((uint64_t)idx >> 32);
+        cz[q] = (uint32_t)tree;
+        cw[q] = (uint32_t)((uint64_t)tree >> 32);  // stream 0, block 0
+    }
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, cx[q]), lo0 = 0xD2511F53u * cx[q];
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, cz[q]), lo1 = 0xCD9E8D57u * cz[q];
+            cx[q] = hi1 ^ cy[q] ^ k0;
+            cy[q] = lo1;
+            cz[q] = hi0 ^ cw[q] ^ k1;
+            cw[q] = lo0;
+        }
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out[q] = cx[q];
 }
 
 // stream 0: random.random() / random.choice / random.randint replacements (helpers.py:51, mcts.py:190-192)

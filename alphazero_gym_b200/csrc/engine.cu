@@ -55,6 +55,8 @@ struct azg_engine {
     float* chead = nullptr;
     int32_t *pw_table = nullptr, *n_rows = nullptr, *draws = nullptr, *leaf = nullptr;
     uint8_t* path = nullptr;
+    uint16_t* dpath = nullptr;  // discrete: recorded path of the current simulation [B][R]
+    int32_t* ddepth = nullptr;
     uint32_t* ctr = nullptr;
     float4* X = nullptr;
     double* root_state = nullptr;
@@ -118,7 +120,7 @@ extern "C" void azg_destroy(azg_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     void* ptrs[] = {e->drows, e->dstate, e->crows, e->hot_block, e->chead, e->pw_table, e->n_rows, e->draws,
-                    e->leaf, e->path, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qfl, e->r_actions,
+                    e->leaf, e->path, e->dpath, e->ddepth, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qfl, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -182,9 +184,9 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
         }
     }
     e->fused = (c.flags & AZG_FLAG_FUSED) != 0;
-    if (e->fused && !(e->q8 && c.variant == AZG_CONTINUOUS && c.state_dim == 3)) {
+    if (e->fused && !(e->q8 && c.state_dim == (c.variant == AZG_CONTINUOUS ? 3 : 4))) {
         delete e;
-        return fail(AZG_EINVAL, "AZG_FLAG_FUSED needs the continuous variant with AZG_FLAG_EVAL_Q8");
+        return fail(AZG_EINVAL, "AZG_FLAG_FUSED needs AZG_FLAG_EVAL_Q8 and the shipped envs (state_dim 3 continuous / 4 discrete)");
     }
     const size_t B = c.max_trees, R = e->R;
     std::vector<int32_t> pwt;
@@ -214,6 +216,8 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     if (c.variant == AZG_DISCRETE) {
         ALLOC(drows, B * R);
         ALLOC(dstate, B * R * 4);
+        ALLOC(dpath, B * R);
+        ALLOC(ddepth, B);
     } else {
         ALLOC(crows, B * R);
         {
@@ -442,7 +446,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.crows = e->crows; p.et = e->et; p.ctl = e->ctl; p.BS = e->cfg.max_trees; p.chead = e->chead;
     p.pw_table = e->pw_table;
     p.rcp_tab = e->dtab; p.sqrt_tab = e->dtab + AZG_TAB + 1;
-    p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path;
+    p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path; p.dpath = e->dpath; p.ddepth = e->ddepth;
     p.ctr = e->ctr; p.X = e->X; p.root_state = e->root_state; p.root_n_init = e->root_n_init; p.err = e->err;
     p.tapeV = e->tapeV; p.tapeP = e->tapeP; p.tapeA = e->tapeA;
     return p;
@@ -524,6 +528,7 @@ static cudaError_t launch_fused(const azg_engine* e, const MlpParams& m, const T
 #define FUSED_CASE(s, a, nl) \
     if (S == s && A == a && NL == nl) return launch_fused_t<s, a, nl>(e, m, p, N, st, launches);
     FUSED_CASE(3, 0, 1) FUSED_CASE(3, 1, 1) FUSED_CASE(3, 0, 2) FUSED_CASE(3, 1, 2)
+    FUSED_CASE(4, 0, 1) FUSED_CASE(4, 1, 1) FUSED_CASE(4, 0, 2) FUSED_CASE(4, 1, 2)
 #undef FUSED_CASE
     return cudaErrorInvalidValue;
 }
@@ -587,6 +592,11 @@ static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStr
         if (ce == cudaSuccess) ce = cudaGetLastError(); \
     } while (0)
     const int tb = 128, tg = (B + tb - 1) / tb;
+    if (e->fused && !tape && !prof) {  // the whole search in one persistent kernel per chunk of trees (qmlp2.cuh, FUSED)
+        ce = launch_fused(e, m, p, N, st, &launches);
+        *cerr = ce;
+        return launches;
+    }
     if (e->cfg.variant == AZG_DISCRETE) {
         LK(2, (k_init_discrete<<<tg, tb, 0, st>>>(p)));
         if (!tape) LK(1, ce = launch_mlp(e, m, st, false));
@@ -597,11 +607,6 @@ static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStr
         }
         LK(0, (k_step_discrete<true, false><<<tg, tb, 0, st>>>(p)));
     } else {
-        if (e->fused && !tape && !prof) {  // the whole search in one persistent kernel per chunk of trees (qmlp2.cuh, FUSED)
-            ce = launch_fused(e, m, p, N, st, &launches);
-            *cerr = ce;
-            return launches;
-        }
         LK(2, (k_init_continuous<<<tg, tb, 0, st>>>(p)));
         if (!tape) LK(1, ce = launch_mlp(e, m, st, false));
         LK(2, (k_root_insert_continuous<<<tg, tb, 0, st>>>(p)));

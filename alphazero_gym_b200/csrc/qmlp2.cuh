@@ -25,6 +25,7 @@
 #pragma once
 #include "qmlp.cuh"
 #include "tree_continuous.cuh"
+#include "tree_discrete.cuh"
 
 #define Q2_EPI_THREADS 512
 #define Q2_THREADS 768                // 16 epilogue warps + the MMA warpgroup + the post-processing warpgroup (registers rebalanced with setmaxnreg)
@@ -283,7 +284,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         for (int i = tid; i <= FUSED_TAB; i += blockDim.x) {
             s_rcp[i] = tp.rcp_tab[i];
             s_sq[i] = tp.sqrt_tab[i];
-            s_pw[i] = i < p.R ? tp.pw_table[i] : 0;  // the table has max_rollouts + 2 = R entries
+            s_pw[i] = (tp.pw_table && i < p.R) ? tp.pw_table[i] : 0;  // continuous only; the table has max_rollouts + 2 = R entries
         }
         __syncthreads();
     }
@@ -391,7 +392,10 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
                 const long long until = cyc_begin + (long long)(blockIdx.x % p.stagger_groups) * p.stagger_ns * 2;  // ~2 cycles per ns
                 while (clock64() < until) __nanosleep(1000);
             }
-            for (int i = tid; i < nrows; i += Q2_EPI_THREADS) c_init(tp, row_begin + i);
+            for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
+                if (S == 4) d_init(tp, row_begin + i);  // state_dim 4 = CartPole = the discrete tree (engine.cu checks it)
+                else c_init(tp, row_begin + i);
+            }
             group_sync(Q2_BAR_PHASE, 640);
         }
         uint32_t fullph = 0;  // bit T: parity of the next wait on full[T]
@@ -485,8 +489,12 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
 #pragma unroll 1
             for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
                 const int gr = row_begin + i;
-                if (s == 0) c_root_insert(tp, gr);                // the add_pw_action(root) before the loop (mcts.py:673)
-                c_step(tp, tabs, gr, s > 0, s + 1 < n_evals);     // backup of simulation s, descent + expansion of simulation s + 1
+                if (S == 4) {
+                    d_step(tp, tabs, gr, s > 0, s + 1 < n_evals);
+                } else {
+                    if (s == 0) c_root_insert(tp, gr);                // the add_pw_action(root) before the loop (mcts.py:673)
+                    c_step(tp, tabs, gr, s > 0, s + 1 < n_evals);     // backup of simulation s, descent + expansion of simulation s + 1
+                }
             }
             group_sync(Q2_BAR_PHASE, 640);
             cyc_sync += c1 - c0;

@@ -21,9 +21,7 @@ __device__ __forceinline__ DRow load_drow(const DRow* p) {
 }
 
 // root row + first network input (MCTSDiscrete.initialize_search, mcts.py:364-383)
-__global__ void k_init_discrete(const TreeParams p) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.B) return;
+__device__ __forceinline__ void d_init(const TreeParams& p, int t) {
     const double* s = p.root_state + (size_t)t * 4;
     double* st = p.dstate + (size_t)t * p.R * 4;
     DRow row;
@@ -51,30 +49,51 @@ __global__ void k_init_discrete(const TreeParams p) {
     p.draws[t] = 0;
     for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
 }
-
-template <bool BACKUP, bool SELECT>
-__global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
+__global__ void k_init_discrete(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= p.B) return;
+    if (t < p.B) d_init(p, t);
+}
+
+// one simulation step of tree t: backup of the previous simulation (BACKUP), then descent + expansion of the next (SELECT).
+// Shared by k_step_discrete (one launch per simulation) and the whole-search kernel (qmlp2.cuh, FUSED).
+__device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int t, const bool BACKUP, const bool SELECT) {
     DRow* rows = p.drows + (size_t)t * p.R;
 
+    uint16_t* path = p.dpath + (size_t)t * p.R;
     if (BACKUP) {
-        // R = leaf.V; up the path: R = node.r + gamma*R; edge.n += 1; edge.W += R; parent.n += 1
+        // R = leaf.V; up the path: R = node.r + gamma*R; edge.n += 1; edge.W += R; parent.n += 1 (mcts.py:241-267).
+        // The select step recorded the path (row, action) root -> leaf, so the row addresses are known up front and the rows are
+        // fetched four at a time; following the parent links instead made every level a dependent L2 round trip, and CartPole
+        // traces are 8 levels deep on average (tens in the deepest tree of a warp).
         const int leaf = p.leaf[t] & LEAF_ROW_MASK;
-        const DRow lr = load_drow(rows + leaf);
-        double Rv = (double)lr.V;
-        double r = lr.r;
-        int parent = lr.parent, pa = lr.paction;
-        while (parent != DROW_NONE) {
-            Rv = r + p.gamma * Rv;
-            DRow* pr = rows + parent;
-            const DRow prow = load_drow(pr);
-            pr->W[pa] = prow.W[pa] + Rv;
-            pr->n_e[pa] = prow.n_e[pa] + 1;
-            pr->node_n = prow.node_n + 1;
-            r = prow.r;
-            pa = prow.paction;
-            parent = prow.parent;
+        const int d = p.ddepth[t];
+        double Rv, r;
+        {
+            const DRow lr = load_drow(rows + leaf);
+            Rv = (double)lr.V;
+            r = lr.r;
+        }
+#pragma unroll 1
+        for (int base = d - 1; base >= 0; base -= 4) {
+            DRow q[4];
+            int pe[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                pe[k] = base - k >= 0 ? (int)path[base - k] : 0;
+                q[k] = load_drow(rows + (pe[k] >> 1));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (base - k >= 0) {
+                    DRow* pr = rows + (pe[k] >> 1);
+                    const int pa = pe[k] & 1;
+                    Rv = r + p.gamma * Rv;
+                    pr->W[pa] = (pa ? q[k].W[1] : q[k].W[0]) + Rv;
+                    pr->n_e[pa] = (pa ? q[k].n_e[1] : q[k].n_e[0]) + 1;
+                    pr->node_n = q[k].node_n + 1;
+                    r = q[k].r;
+                }
+            }
         }
     }
 
@@ -85,22 +104,33 @@ __global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
         DRow row = load_drow(rows);
         int a = -1;
         uint32_t levels = 0;
+        uint32_t xr[4] = {0, 0, 0, 0};
         bool nan = false;
         while (true) {
+            // both children are requested while the scores are computed: the chosen one is then a cache hit instead of a
+            // dependent round trip per level
+            if (row.child[0] != DROW_NONE) asm volatile("prefetch.global.L1 [%0];" ::"l"(rows + row.child[0]));
+            if (row.child[1] != DROW_NONE) asm volatile("prefetch.global.L1 [%0];" ::"l"(rows + row.child[1]));
             // UCT_a = Q_a + prior_a*c_uct*(sqrt(node.n+1)/(n_a+1))   (mcts.py:483-484)
-            const double sq = sqrt_small(row.node_n + 1, p.sqrt_tab, AZG_TAB);
+            const double sq = sqrt_small(row.node_n + 1, tb.sq, tb.n);
             double u[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int n = row.n_e[i];
-                const double Q = n > 0 ? div_small(row.W[i], n, p.rcp_tab, AZG_TAB) : (double)row.V;
+                const double Q = n > 0 ? div_small(row.W[i], n, tb.rcp, tb.n) : (double)row.V;
                 const double pc = p.puct_f32 ? (double)__fmul_rn(row.prior[i], (float)p.c_uct) : (double)row.prior[i] * p.c_uct;
-                u[i] = Q + pc * div_small(sq, n + 1, p.rcp_tab, AZG_TAB);
+                u[i] = Q + pc * div_small(sq, n + 1, tb.rcp, tb.n);
             }
             nan |= (u[0] != u[0]) || (u[1] != u[1]);
             bool random_pick = false;
             if (p.epsilon != 0) {  // epsilon_greedy: random.random() < eps -> random.randint(0, A-1)
-                const double x = (double)u32_to_unit(rng_select_u32(p, tree, draws++));
+                // every level consumes exactly two draws (random(), then randint or choice), so the random() of the next four
+                // levels are draws + 0, 2, 4, 6: generated together (the generator was half of a level's dependent chain)
+                const int k = (int)(levels & 3u);
+                if (k == 0) rng_select_u32x4(__ldg(p.seedp), tree, draws, 2, xr);
+                const uint32_t xk = k == 0 ? xr[0] : (k == 1 ? xr[1] : (k == 2 ? xr[2] : xr[3]));
+                ++draws;
+                const double x = (double)u32_to_unit(xk);
                 random_pick = x < p.epsilon;
             }
             if (random_pick) {
@@ -111,6 +141,7 @@ __global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
                 else a = u[1] > u[0] ? 1 : 0;
                 ++draws;
             }
+            path[levels] = (uint16_t)((cur << 1) | a);
             ++levels;
             const int child = row.child[a];
             if (child == DROW_NONE) break;  // expansion
@@ -119,6 +150,7 @@ __global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
             if (row.flags & ROW_TERMINAL) { a = -1; break; }  // trace ends on an existing terminal node
         }
         if (nan) atomicOr(p.err, ERR_NAN);
+        p.ddepth[t] = (int)levels;  // edges between the root and the leaf (the new node, or the existing terminal node the trace ended on)
         p.draws[t] = draws;
         p.ctr[t] += levels;
         p.ctr[(size_t)p.B + t] += levels * 2;
@@ -159,6 +191,13 @@ __global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
             p.ctr[(size_t)2 * p.B + t] += 1;
         }
     }
+}
+
+template <bool BACKUP, bool SELECT>
+__global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const Tabs tb = {p.pw_table, p.rcp_tab, p.sqrt_tab, AZG_TAB};
+    if (t < p.B) d_step(p, tb, t, BACKUP, SELECT);
 }
 
 // MCTS.return_results (mcts.py:269-307) for the discrete root

@@ -43,7 +43,7 @@ class EngineConfig:
     seed: int = 34
     use_graph: bool = True
     eval_q8: bool = False  # AZG_FLAG_EVAL_Q8: hidden x hidden layers on tcgen05 as exact int8-sliced products (include/azg.h)
-    fused: Optional[bool] = None  # AZG_FLAG_FUSED: whole search in one persistent kernel; None = on where supported (continuous + eval_q8)
+    fused: Optional[bool] = None  # AZG_FLAG_FUSED: whole search in one persistent kernel; None = on where supported (eval_q8)
 
     def c(self) -> AzgConfig:
         return AzgConfig(self.variant, self.max_rollouts, self.max_trees, self.num_actions, self.num_components,
@@ -54,7 +54,7 @@ class EngineConfig:
                          | (_cabi.FLAG_FUSED if self.is_fused() else 0), self.seed)
 
     def is_fused(self) -> bool:
-        supported = bool(self.eval_q8) and self.variant == CONTINUOUS
+        supported = bool(self.eval_q8) and self.state_dim == (3 if self.variant == CONTINUOUS else 4)
         return supported if self.fused is None else bool(self.fused)
 
 

@@ -71,7 +71,7 @@ def engine_config(variant: str, B: int, N: int, device: int, q8: bool = False, f
     from alphazero_gym_b200._cabi import ACT_ELU, ACT_RELU, CONTINUOUS, DISCRETE
     if variant == "discrete":  # run_discrete.yaml / MCTSDiscrete.yaml / DiscretePolicy.yaml
         return EngineConfig(variant=DISCRETE, max_rollouts=N, max_trees=B, num_actions=2, state_dim=4, hidden=128, n_hidden=2,
-                            activation=ACT_RELU, c_uct=1.5, gamma=1.0, epsilon=0.1, device=device, seed=34, eval_q8=q8)
+                            activation=ACT_RELU, c_uct=1.5, gamma=1.0, epsilon=0.1, device=device, seed=34, eval_q8=q8, fused=fused)
     return EngineConfig(variant=CONTINUOUS, max_rollouts=N, max_trees=B, num_components=2, state_dim=3, hidden=128, n_hidden=3,
                         activation=ACT_ELU, c_uct=0.05, c_pw=1.0, kappa=0.5, gamma=1.0, epsilon=0.0, action_bound=2.0,
                         device=device, seed=34, eval_q8=q8, fused=fused)
@@ -390,7 +390,7 @@ def main():
         tflops = flop / (k_ms * 1e-3) / 1e12
         ev_ms, tree_ms = k_ms * (1.0 - st["tree_phase"]), k_ms * st["tree_phase"]
         tbytes = algorithmic_bytes(variant, fc) / max(1, counters["launches"])
-        hh = 2 * 128 * 128 * 2
+        hh = 2 * 128 * 128 * ((3 if variant == "continuous" else 2) - 1)
         dominant = {
             "kernel": "k_qmlp2<FUSED> (whole search in one persistent kernel: per simulation an evaluation phase on tcgen05 kind::i8 "
                       "and a tree phase, backup + select + expansion, one thread per tree)",

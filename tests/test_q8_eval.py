@@ -116,11 +116,7 @@ def test_q8_kernel_equals_oracle_bit_exact(name, n):
 
 
 def _fused_kw(cfg, fused):
-    """AZG_FLAG_FUSED (whole search in one persistent kernel) exists for the continuous variant only."""
-    if cfg.variant == azo.DISCRETE:
-        if fused:
-            pytest.skip("the whole-search kernel serves the continuous variant")
-        return {}
+    """AZG_FLAG_FUSED: the whole search in one persistent kernel, or one launch per kernel and simulation."""
     return {"fused": fused}
 
 
