@@ -465,12 +465,6 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     m.head_dim = azg_head_dim(e);
     m.qdigits = e->qdigits; m.qfl = e->qfl; m.qfl_count = e->qfl_count;
     m.stats = e->stats;
-    {
-        const char* g = getenv("AZG_STAGGER_GROUPS");
-        const char* ns = getenv("AZG_STAGGER_NS");
-        m.stagger_groups = g ? atoi(g) : 1;
-        m.stagger_ns = ns ? atoi(ns) : 0;
-    }
     return m;
 }
 

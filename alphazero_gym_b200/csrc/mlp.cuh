@@ -53,9 +53,6 @@ struct MlpParams {
     int32_t qfl_count;  // floats in qfl (multiple of 4)
     // whole-search kernel: cycle accounting, summed over CTAs (azg_fused_stats, include/azg.h)
     unsigned long long* stats;
-    // whole-search kernel: CTA b starts (b % stagger_groups) * stagger_ns late, so that the tree phases of the groups (HBM-bound
-    // random access) do not fall on top of each other while their evaluations (no HBM traffic) do not care
-    int32_t stagger_groups, stagger_ns;
 };
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP / SYNCS) --------------

@@ -248,13 +248,9 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
     const int nrows = row_end - row_begin;
     int ntiles = (nrows + 127) / 128;
     if (ntiles > 1) ntiles = (ntiles + 1) & ~1;
-#ifdef Q2_EQUAL_TILES
-    const int th = (nrows + ntiles - 1) / ntiles;
-#else
     // full tiles first, the remainder in the last one(s): epilogue work is spent per 32-row group, so 443 rows cost 14 row groups
     // as 128 + 128 + 128 + 59 against 16 as four tiles of 111 (the warps of the empty row groups leave their issue slots to the others)
     const int th = 128;
-#endif
 
     if (tid == 0) {
         mbar_init(&wbar, 1);
@@ -388,10 +384,6 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         const long long cyc_begin = clock64();
         const Tabs tabs = {s_pw, s_rcp, s_sq, FUSED_TAB};
         if (FUSED) {  // MCTSContinuous.initialize_search for every tree of the CTA
-            if (p.stagger_groups > 1) {
-                const long long until = cyc_begin + (long long)(blockIdx.x % p.stagger_groups) * p.stagger_ns * 2;  // ~2 cycles per ns
-                while (clock64() < until) __nanosleep(1000);
-            }
             for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
                 if (S == 4) d_init(tp, row_begin + i);  // state_dim 4 = CartPole = the discrete tree (engine.cu checks it)
                 else c_init(tp, row_begin + i);
