@@ -1,0 +1,107 @@
+"""Training step: alphazero_gym_b200.train.Trainer against the unmodified reference's Agent.update.
+
+The goldens (tests/golden/train_*.npz) come from oracle/gen_train_golden.py, which runs ContinuousAgent.update /
+DiscreteAgent.update of /root/reference with its own policies, losses and torch optimizers for three consecutive steps.
+Bar: every loss component within 1e-5 relative (+1e-6 absolute) at every step; final weights within 2e-6 absolute (the
+optimizers divide by sqrt(v) + eps with eps = 1e-10 / 1e-7, so a last-bit difference in a near-zero gradient is a visible
+difference in the step: at most 0.1 % of the weights may deviate more, and none by more than two learning-rate steps).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from alphazero_gym_b200.network import PolicyNet
+from alphazero_gym_b200.train import LossConfig, Trainer
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CASES = {
+    "train_a0c_tuned_rmsprop": dict(net=dict(state_dim=3, hidden=128, n_hidden=3, head_dim=6, nonlinearity="elu", num_components=2),
+                                    loss=LossConfig(tuned=True, tau=0.1, policy_coeff=0.1, value_coeff=1, alpha=1, reduction="mean"),
+                                    opt="rmsprop", clip=0.0),
+    "train_a0c_adam_clip": dict(net=dict(state_dim=3, hidden=128, n_hidden=3, head_dim=6, nonlinearity="elu", num_components=2),
+                                loss=LossConfig(tuned=False, tau=0.1, policy_coeff=1, value_coeff=1, alpha=1, reduction="mean"),
+                                opt="adam", clip=0.5),
+    "train_a0c_k1_sum": dict(net=dict(state_dim=3, hidden=128, n_hidden=3, head_dim=2, nonlinearity="elu", num_components=1),
+                             loss=LossConfig(tuned=False, tau=0.5, policy_coeff=0.3, value_coeff=2, alpha=0.2, reduction="sum"),
+                             opt="adam", clip=0.0),
+    "train_a0c_discrete_rmsprop": dict(net=dict(state_dim=4, hidden=128, n_hidden=2, head_dim=2, nonlinearity="relu", num_actions=2),
+                                       loss=LossConfig(tuned=False, tau=0.1, policy_coeff=1, value_coeff=1, alpha=1, reduction="mean"),
+                                       opt="rmsprop", clip=0.0),
+    "train_a0c_discrete_adam": dict(net=dict(state_dim=4, hidden=128, n_hidden=2, head_dim=2, nonlinearity="relu", num_actions=2),
+                                    loss=LossConfig(tuned=False, tau=0.1, policy_coeff=1, value_coeff=1, alpha=0.05, reduction="mean"),
+                                    opt="adam", clip=1.0),
+}
+
+
+def _run(name, device, cuda_graph=False):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    c = CASES[name]
+    torch.manual_seed(0)
+    net = PolicyNet(**c["net"]).load_flat(g["w0"]).to(device)
+    tr = Trainer(net, c["loss"], optimizer=c["opt"], grad_clip=c["clip"], cuda_graph=cuda_graph)
+    infos = []
+    for s in range(3):
+        batch = dict(obs=torch.from_numpy(g[f"states_{s}"]).to(device), actions=torch.from_numpy(g[f"actions_{s}"]).to(device),
+                     counts=torch.from_numpy(g[f"counts_{s}"]).to(device), V_target=torch.from_numpy(g[f"V_{s}"]).to(device))
+        infos.append({k: float(v) for k, v in tr.update(batch).items()})
+    return g, tr, infos
+
+
+def _check(name, device, loss_rtol, w_atol, cuda_graph=False):
+    g, tr, infos = _run(name, device, cuda_graph)
+    for s, info in enumerate(infos):
+        for k, v in info.items():
+            ref = float(g[f"info_{k}_{s}"])
+            assert abs(v - ref) <= loss_rtol * abs(ref) + 1e-6, (name, s, k, v, ref)
+    w, ref = tr.flat_weights().cpu().numpy(), g["w_3"]
+    d = np.abs(w - ref)
+    assert (d > w_atol).mean() <= 1e-3 and d.max() <= 2.5e-3, (name, float((d > w_atol).mean()), float(d.max()))
+    if "log_alpha_3" in g.files:
+        assert abs(float(tr.loss.log_alpha.detach()) - float(g["log_alpha_3"])) <= 1e-6
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_update_matches_reference_cpu(name):
+    torch.set_num_threads(1)
+    _check(name, "cpu", 1e-5, 2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_update_matches_reference_gpu(name):
+    """The same step on cuda:0 (cuBLAS GEMMs sum in a different order: losses within 1e-4, weights within 2e-5)."""
+    _check(name, "cuda:0", 1e-4, 2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_graph_captured_update_matches_reference_gpu(name):
+    """The whole step replayed from a CUDA graph (Trainer(cuda_graph=True)): three replays = the reference's three steps, i.e. the
+    warm-up steps of the capture leave no trace in weights or optimizer state."""
+    _check(name, "cuda:0", 1e-4, 2e-5, cuda_graph=True)
+
+
+@pytest.mark.gpu
+def test_trained_weights_reach_the_search_engine():
+    """Trainer.push_weights -> azg_set_weights: a search after the update uses the new network (root V changes, and equals
+    the network's own value of the root observation)."""
+    from alphazero_gym_b200._cabi import ACT_ELU, CONTINUOUS
+    from alphazero_gym_b200.engine import EngineConfig, SearchEngine
+    name = "train_a0c_tuned_rmsprop"
+    g, tr, _ = _run(name, "cuda:0")
+    eng = SearchEngine(EngineConfig(variant=CONTINUOUS, max_rollouts=25, max_trees=64, num_components=2, state_dim=3, hidden=128,
+                                    n_hidden=3, activation=ACT_ELU, c_uct=0.05))
+    try:
+        x = np.stack([np.cos(0.3), np.sin(0.3), 0.5])[None].astype(np.float32)
+        eng.set_weights(g["w0"])
+        v0, _ = eng.mlp_forward(x)
+        tr.push_weights(eng)
+        v1, _ = eng.mlp_forward(x)
+        with torch.no_grad():
+            vt = float(tr.net.value_head(tr.net.trunk(torch.from_numpy(x).cuda())))
+        assert abs(float(v1[0]) - vt) <= 1e-5 * abs(vt) + 1e-6 and abs(float(v1[0]) - float(v0[0])) > 1e-5
+    finally:
+        eng.close()
