@@ -151,6 +151,12 @@ def make_optimizer(name: str, params, lr: float = 0.001, capturable: bool = Fals
     raise ValueError(f"unknown optimizer {name}")
 
 
+def root_children(c_pw: float, kappa: float, n_rollouts: int) -> int:
+    """Children of the root after a finished continuous search: the progressive-widening limit at the last root visit count
+    (states.py:252-275 with n = n_rollouts - 1)."""
+    return int(math.ceil(c_pw * float(n_rollouts) ** kappa))
+
+
 class Trainer:
     """`Agent.update` on device tensors + hand-over of the new weights to a SearchEngine.
 
@@ -158,8 +164,11 @@ class Trainer:
     batches: dicts with the DeviceReplayBuffer keys (obs, actions, counts, V_target)."""
 
     def __init__(self, net: PolicyNet, loss: LossConfig, optimizer: str = "rmsprop", lr: float = 0.001, grad_clip: float = 0.0,
-                 cuda_graph: bool = False):
-        """cuda_graph=True (CUDA devices): `update` captures the whole step -- forward, backward, both optimizer steps -- into a CUDA
+                 cuda_graph: bool = False, n_root_actions: Optional[int] = None):
+        """n_root_actions: the engine pads root-result rows to azg_cmax columns (count 0, action 0); the reference's rows hold exactly the
+        root's children -- ceil(c_pw * n_rollouts^kappa) for the continuous search (`root_children`), the action count for the discrete
+        one -- and log(0) would poison the loss, so only the first n_root_actions columns are used when it is given.
+        cuda_graph=True (CUDA devices): `update` captures the whole step -- forward, backward, both optimizer steps -- into a CUDA
         graph on its first call for a batch shape and replays it afterwards: the step is ~150 small kernels, i.e. launch-bound
         (2.1 ms eager at any batch size up to 64 K rows, tools/train_bench.py)."""
         self.net = net
@@ -169,11 +178,14 @@ class Trainer:
         self.opt = make_optimizer(optimizer, net.parameters(), lr, capturable=self.cuda_graph)
         self.clip = grad_clip
         self.discrete = bool(net.num_actions)
+        self.n_root_actions = n_root_actions
         self._graphs: Dict[tuple, tuple] = {}
 
     def update(self, batch: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         """One gradient step; returns the loss components as 0-d device tensors (no host synchronisation except, without
         cuda_graph, A0CLossTuned's `alpha.item()`, which the reference has as well)."""
+        if self.n_root_actions is not None:
+            batch = dict(batch, actions=batch["actions"][:, :self.n_root_actions], counts=batch["counts"][:, :self.n_root_actions])
         if not self.cuda_graph:
             return self._step(batch)
         key = tuple((k, tuple(batch[k].shape), batch[k].dtype) for k in ("obs", "actions", "counts", "V_target"))

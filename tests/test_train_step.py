@@ -105,3 +105,46 @@ def test_trained_weights_reach_the_search_engine():
         assert abs(float(v1[0]) - vt) <= 1e-5 * abs(vt) + 1e-6 and abs(float(v1[0]) - float(v0[0])) > 1e-5
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_selfplay_replay_train_loop_on_device():
+    """Ranks 1-3 of SURVEY 8(f) together, nothing leaving the GPU: batched self-play steps fill the device replay buffer, the
+    trainer consumes shuffled mini-batches from it (graph-replayed steps), the new weights go back into the engine, and the
+    next search runs with them.  Checks the bookkeeping (visit counts add up before and after the weight change, losses finite,
+    weights moved, the engine evaluates with exactly the trainer's weights)."""
+    from alphazero_gym_b200._cabi import ACT_ELU, CONTINUOUS
+    from alphazero_gym_b200.engine import EngineConfig, SearchEngine
+    from alphazero_gym_b200.network import init_policy_weights
+    from alphazero_gym_b200.selfplay import DeviceReplayBuffer, SelfPlayDriver
+    B, N = 512, 25
+    eng = SearchEngine(EngineConfig(variant=CONTINUOUS, max_rollouts=N, max_trees=B, num_components=2, state_dim=3, hidden=128,
+                                    n_hidden=3, activation=ACT_ELU, c_uct=0.05, eval_q8=True))
+    try:
+        w0 = init_policy_weights(34, 3, 128, 3, 6)
+        net = PolicyNet(3, 128, 3, 6, "elu", num_components=2).load_flat(w0).cuda()
+        from alphazero_gym_b200.train import root_children
+        assert root_children(1.0, 0.5, N) == 5 and eng.cmax >= 5
+        tr = Trainer(net, LossConfig(tuned=True), optimizer="rmsprop", cuda_graph=True, n_root_actions=root_children(1.0, 0.5, N))
+        tr.push_weights(eng)
+        replay = DeviceReplayBuffer(max_size=4 * B, batch_size=256, obs_dim=3, cmax=eng.cmax, device=eng.device)
+        drv = SelfPlayDriver(eng, B, N, max_episode_length=200, seed=34, replay=replay)
+        for _ in range(3):
+            out = drv.step()
+            assert int(out["counts"].sum()) == B * N and int(out["n_children"].min()) == 5 and int(out["n_children"].max()) == 5
+        assert replay.size == 3 * B
+        replay.reshuffle(torch.Generator(device=eng.device).manual_seed(1))
+        losses = [float(tr.update(b)["loss"]) for b in replay]
+        assert len(losses) == 6 and all(np.isfinite(losses))
+        w1 = tr.flat_weights()
+        assert float((w1.cpu() - torch.from_numpy(w0)).abs().max()) > 1e-4
+        tr.push_weights(eng)
+        x = np.array([[np.cos(1.0), np.sin(1.0), -2.0]], np.float32)
+        v_eng, _ = eng.mlp_forward(x)
+        with torch.no_grad():
+            v_net = float(net.value_head(net.trunk(torch.from_numpy(x).cuda())))
+        assert abs(float(v_eng[0]) - v_net) <= 1e-5 * abs(v_net) + 1e-6
+        out = drv.step()
+        assert int(out["counts"].sum()) == B * N
+    finally:
+        eng.close()
