@@ -18,6 +18,7 @@ VT = {"off_policy": 0, "on_policy": 1, "greedy": 2}
 FLAG_NO_GRAPH = 1
 FLAG_EVAL_Q8 = 2
 FLAG_FUSED = 4
+FLAG_RNG_MT19937 = 8
 
 EXPORTS = [
     "azg_create", "azg_destroy", "azg_last_error", "azg_version", "azg_num_weights", "azg_set_weights",

@@ -123,6 +123,8 @@ struct TreeParams {
     int32_t* draws;   // selection RNG draw counter (stream 0)
     int32_t* leaf;    // LEAF_* word
     uint8_t* path;    // [B][R] continuous: path entries beyond the 16 held in CCtl
+    uint32_t* mt;     // [B][625] AZG_FLAG_RNG_MT19937 (discrete): per-tree MT19937 state + index word (see mt19937 below)
+    int32_t rng_mt;
     uint16_t* dpath;  // [B][R] discrete: the current simulation's path, (row << 1 | action) per level, root first (read by the backup)
     int32_t* ddepth;  // [B]    discrete: its length
     uint32_t* ctr;    // [4][B]: levels, children scanned, terminal-leaf sims, evals
@@ -222,6 +224,58 @@ __device__ __forceinline__ void rng_select_u32x4(uint64_t seed, int64_t tree, in
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) out[q] = cx[q];
+}
+
+// ---- AZG_FLAG_RNG_MT19937: CPython's generator for the selection draws of the discrete search, so that an
+// UN-SHIMMED reference run (stock `random` module, random.seed(seed + tree) right before MCTSDiscrete.search) is reproduced bit for
+// bit: init_by_array seeding (CPython random_seed with an int), random() = 53 bits of two outputs, choice / randint =
+// _randbelow_with_getrandbits (k = n.bit_length(); take the top k bits until < n).  Same contract as oracle/azg_oracle.c
+// "AZO_RNG_MT19937"; a compatibility mode, not a fast path (2.5 KB of state per tree in HBM).
+#define MT_N 624
+__device__ __forceinline__ void mt_seed_dev(uint32_t* mt, uint64_t seed) {
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const int klen = key[1] ? 2 : 1;
+    mt[0] = 19650218u;
+    for (int i = 1; i < MT_N; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1, j = 0;
+    for (int k = MT_N; k; --k) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        ++i; ++j;
+        if (i >= MT_N) { mt[0] = mt[MT_N - 1]; i = 1; }
+        if (j >= klen) j = 0;
+    }
+    for (int k = MT_N - 1; k; --k) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        ++i;
+        if (i >= MT_N) { mt[0] = mt[MT_N - 1]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+    mt[MT_N] = MT_N;  // index word: the first output regenerates the state
+}
+__device__ __forceinline__ uint32_t mt_next_dev(uint32_t* mt, int& mti, int& draws) {
+    if (mti >= MT_N) {
+        int kk;
+        uint32_t y;
+        for (kk = 0; kk < MT_N - 397; ++kk) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        for (; kk < MT_N - 1; ++kk) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + (397 - MT_N)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        y = (mt[MT_N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[MT_N - 1] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        mti = 0;
+    }
+    uint32_t y = mt[mti++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    ++draws;
+    return y;
+}
+__device__ __forceinline__ double mt_random_dev(uint32_t* mt, int& mti, int& draws) {  // random.random()
+    const uint32_t a = mt_next_dev(mt, mti, draws) >> 5, b = mt_next_dev(mt, mti, draws) >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ int mt_below_dev(uint32_t* mt, int& mti, int& draws, int n) {  // random.choice over n items / randint(0, n - 1)
+    const int k = 32 - __clz(n);  // n.bit_length()
+    uint32_t r = mt_next_dev(mt, mti, draws) >> (32 - k);
+    while ((int)r >= n) r = mt_next_dev(mt, mti, draws) >> (32 - k);
+    return (int)r;
 }
 
 // stream 0: random.random() / random.choice / random.randint replacements (helpers.py:51, mcts.py:190-192)

@@ -55,6 +55,7 @@ struct azg_engine {
     float* chead = nullptr;
     int32_t *pw_table = nullptr, *n_rows = nullptr, *draws = nullptr, *leaf = nullptr;
     uint8_t* path = nullptr;
+    uint32_t* mt = nullptr;     // AZG_FLAG_RNG_MT19937: [B][625]
     uint16_t* dpath = nullptr;  // discrete: recorded path of the current simulation [B][R]
     int32_t* ddepth = nullptr;
     uint32_t* ctr = nullptr;
@@ -120,7 +121,7 @@ extern "C" void azg_destroy(azg_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     void* ptrs[] = {e->drows, e->dstate, e->crows, e->hot_block, e->chead, e->pw_table, e->n_rows, e->draws,
-                    e->leaf, e->path, e->dpath, e->ddepth, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qfl, e->r_actions,
+                    e->leaf, e->path, e->dpath, e->ddepth, e->mt, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qfl, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -183,6 +184,10 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
             return fail(AZG_EINVAL, "AZG_FLAG_EVAL_Q8 needs hidden = 128, n_hidden in {2, 3}, at most 15 head outputs and an sm_100 device (tcgen05)");
         }
     }
+    if ((c.flags & AZG_FLAG_RNG_MT19937) && c.variant != AZG_DISCRETE) {
+        delete e;
+        return fail(AZG_EINVAL, "AZG_FLAG_RNG_MT19937 serves the discrete search only (the continuous one also draws from torch's generator)");
+    }
     e->fused = (c.flags & AZG_FLAG_FUSED) != 0;
     if (e->fused && !(e->q8 && c.state_dim == (c.variant == AZG_CONTINUOUS ? 3 : 4))) {
         delete e;
@@ -218,6 +223,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
         ALLOC(dstate, B * R * 4);
         ALLOC(dpath, B * R);
         ALLOC(ddepth, B);
+        if (c.flags & AZG_FLAG_RNG_MT19937) ALLOC(mt, B * (MT_N + 1));
     } else {
         ALLOC(crows, B * R);
         {
@@ -446,7 +452,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.crows = e->crows; p.et = e->et; p.ctl = e->ctl; p.BS = e->cfg.max_trees; p.chead = e->chead;
     p.pw_table = e->pw_table;
     p.rcp_tab = e->dtab; p.sqrt_tab = e->dtab + AZG_TAB + 1;
-    p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path; p.dpath = e->dpath; p.ddepth = e->ddepth;
+    p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path; p.dpath = e->dpath; p.ddepth = e->ddepth; p.mt = e->mt; p.rng_mt = e->mt != nullptr;
     p.ctr = e->ctr; p.X = e->X; p.root_state = e->root_state; p.root_n_init = e->root_n_init; p.err = e->err;
     p.tapeV = e->tapeV; p.tapeP = e->tapeP; p.tapeA = e->tapeA;
     return p;

@@ -47,6 +47,7 @@ __device__ __forceinline__ void d_init(const TreeParams& p, int t) {
     p.leaf[t] = 0 | LEAF_EVAL;
     p.n_rows[t] = 1;
     p.draws[t] = 0;
+    if (p.rng_mt) mt_seed_dev(p.mt + (size_t)t * (MT_N + 1), __ldg(p.seedp) + (uint64_t)(p.tree_id0 + t));  // random.seed(seed + tree)
     for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
 }
 __global__ void k_init_discrete(const TreeParams p) {
@@ -105,6 +106,8 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
         int a = -1;
         uint32_t levels = 0;
         uint32_t xr[4] = {0, 0, 0, 0};
+        uint32_t* mt = p.rng_mt ? p.mt + (size_t)t * (MT_N + 1) : nullptr;
+        int mti = p.rng_mt ? (int)mt[MT_N] : 0;
         bool nan = false;
         while (true) {
             // both children are requested while the scores are computed: the chosen one is then a cache hit instead of a
@@ -123,7 +126,9 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
             }
             nan |= (u[0] != u[0]) || (u[1] != u[1]);
             bool random_pick = false;
-            if (p.epsilon != 0) {  // epsilon_greedy: random.random() < eps -> random.randint(0, A-1)
+            if (p.epsilon != 0 && p.rng_mt) {
+                random_pick = mt_random_dev(mt, mti, draws) < p.epsilon;
+            } else if (p.epsilon != 0) {  // epsilon_greedy: random.random() < eps -> random.randint(0, A-1)
                 // every level consumes exactly two draws (random(), then randint or choice), so the random() of the next four
                 // levels are draws + 0, 2, 4, 6: generated together (the generator was half of a level's dependent chain)
                 const int k = (int)(levels & 3u);
@@ -133,7 +138,11 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
                 const double x = (double)u32_to_unit(xk);
                 random_pick = x < p.epsilon;
             }
-            if (random_pick) {
+            if (p.rng_mt) {  // randint(0, 1), or choice over the 1 or 2 winners (which also draws for a single winner)
+                if (random_pick) a = mt_below_dev(mt, mti, draws, 2);
+                else if (u[0] == u[1]) a = mt_below_dev(mt, mti, draws, 2);
+                else { (void)mt_below_dev(mt, mti, draws, 1); a = u[1] > u[0] ? 1 : 0; }
+            } else if (random_pick) {
                 a = u32_to_index(rng_select_u32(p, tree, draws++), 2);
             } else {
                 // argmax with random tie-break: one draw is consumed even for a single winner
@@ -150,6 +159,7 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
             if (row.flags & ROW_TERMINAL) { a = -1; break; }  // trace ends on an existing terminal node
         }
         if (nan) atomicOr(p.err, ERR_NAN);
+        if (p.rng_mt) mt[MT_N] = (uint32_t)mti;
         p.ddepth[t] = (int)levels;  // edges between the root and the leaf (the new node, or the existing terminal node the trace ended on)
         p.draws[t] = draws;
         p.ctr[t] += levels;

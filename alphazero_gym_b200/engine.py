@@ -43,6 +43,7 @@ class EngineConfig:
     seed: int = 34
     use_graph: bool = True
     eval_q8: bool = False  # AZG_FLAG_EVAL_Q8: hidden x hidden layers on tcgen05 as exact int8-sliced products (include/azg.h)
+    rng_mt19937: bool = False  # AZG_FLAG_RNG_MT19937: CPython's generator for the discrete search's selection draws (include/azg.h)
     fused: Optional[bool] = None  # AZG_FLAG_FUSED: whole search in one persistent kernel; None = on where supported (eval_q8)
 
     def c(self) -> AzgConfig:
@@ -51,7 +52,7 @@ class EngineConfig:
                          self.puct_f32, self.device, self.c_uct, float(self.gamma), self.epsilon, self.c_pw, self.kappa,
                          self.action_bound, self.log_std_min, self.log_std_max,
                          (0 if self.use_graph else _cabi.FLAG_NO_GRAPH) | (_cabi.FLAG_EVAL_Q8 if self.eval_q8 else 0)
-                         | (_cabi.FLAG_FUSED if self.is_fused() else 0), self.seed)
+                         | (_cabi.FLAG_FUSED if self.is_fused() else 0) | (_cabi.FLAG_RNG_MT19937 if self.rng_mt19937 else 0), self.seed)
 
     def is_fused(self) -> bool:
         supported = bool(self.eval_q8) and self.state_dim == (3 if self.variant == CONTINUOUS else 4)

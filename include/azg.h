@@ -73,6 +73,11 @@ typedef struct azg_config {
                                 evaluation of the other.  Same arithmetic, same results bit for bit as the per-simulation
                                 launches. */
 
+#define AZG_FLAG_RNG_MT19937 8u /* discrete variant: the tie-break / eps-greedy draws come from CPython's MT19937 (seeded like
+                                   random.seed(seed + global tree id) at the start of every search; random(), choice and randint with
+                                   CPython's algorithms) instead of the Philox streams, so that a reference run with its stock
+                                   `random` module is reproduced bit for bit (helpers.py:50-51, mcts.py:190-192) */
+
 typedef struct azg_engine azg_engine;
 
 int azg_create(const azg_config* cfg, azg_engine** out);

@@ -536,9 +536,69 @@ int32_t azo_pw_limit(double c_pw, double kappa, int32_t n) { return (int32_t)cei
 /* ------------------------------------------------------------------------------------------------
  * Selection helpers.
  * ---------------------------------------------------------------------------------------------- */
-typedef struct { uint64_t seed; int64_t tree; int64_t draws; int64_t pw; } rng_t;
+typedef struct { uint64_t seed; int64_t tree; int64_t draws; int64_t pw; int mt_mode; int mti; uint32_t mt[624]; } rng_t;
 
 static inline uint32_t rng_next(rng_t* g) { return azo_rng_u32(g->seed, g->tree, 0, g->draws++, 0, 0); }
+
+/* AZO_RNG_MT19937 (config.rng_mode = 1): the selection draws come from CPython's own generator, so that an
+ * UN-SHIMMED reference run -- stock `random` module, `random.seed(seed + tree)` right before MCTSDiscrete.search -- is reproduced:
+ * MT19937 seeded by init_by_array (CPython random_seed with an int), random() = 53 bits from two outputs, choice / randint =
+ * _randbelow_with_getrandbits (k = n.bit_length(); draw the top k bits until < n).  `draws` counts generator outputs. */
+static void mt_init_genrand(uint32_t* mt, uint32_t s) {
+    mt[0] = s;
+    for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+}
+static void mt_seed(rng_t* g, uint64_t seed) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const int klen = key[1] ? 2 : 1;
+    uint32_t* mt = g->mt;
+    mt_init_genrand(mt, 19650218u);
+    int i = 1, j = 0;
+    for (int k = 624 > klen ? 624 : klen; k; --k) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        ++i; ++j;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+        if (j >= klen) j = 0;
+    }
+    for (int k = 623; k; --k) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        ++i;
+        if (i >= 624) { mt[0] = mt[623]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+    g->mti = 624;
+}
+static uint32_t mt_next(rng_t* g) {
+    uint32_t* mt = g->mt;
+    if (g->mti >= 624) {
+        int kk;
+        uint32_t y;
+        for (kk = 0; kk < 624 - 397; ++kk) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        for (; kk < 623; ++kk) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        g->mti = 0;
+    }
+    uint32_t y = mt[g->mti++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    g->draws++;
+    return y;
+}
+/* random.random() */
+static double rng_random(rng_t* g) {
+    if (!g->mt_mode) return (double)u32_to_unit(rng_next(g));
+    const uint32_t a = mt_next(g) >> 5, b = mt_next(g) >> 6;
+    return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+}
+/* random.choice over n items / random.randint(0, n - 1) */
+static int rng_below(rng_t* g, int n) {
+    if (!g->mt_mode) return u32_to_index(rng_next(g), n);
+    int k = 0;
+    while ((n >> k) != 0) ++k; /* n.bit_length() */
+    uint32_t r = mt_next(g) >> (32 - k);
+    while ((int)r >= n) r = mt_next(g) >> (32 - k);
+    return (int)r;
+}
 
 /* helpers.py:30-52: winners = where(x == max(x)); random.choice(winners) -- one draw even for one winner */
 static int argmax_tiebreak(const double* x, int n, rng_t* g, int* err) {
@@ -548,7 +608,7 @@ static int argmax_tiebreak(const double* x, int n, rng_t* g, int* err) {
     if (nan) { *err = -3; return 0; }
     int nw = 0;
     for (int i = 0; i < n; ++i) nw += (x[i] == m);
-    int pick = u32_to_index(rng_next(g), nw);
+    int pick = rng_below(g, nw);
     for (int i = 0; i < n; ++i) if (x[i] == m && pick-- == 0) return i;
     return 0;
 }
@@ -556,8 +616,8 @@ static int argmax_tiebreak(const double* x, int n, rng_t* g, int* err) {
 /* mcts.py:488-493 / :736-741 + epsilon_greedy :175-195 */
 static int select_index(const azo_config* c, const double* uct, int n, rng_t* g, int* err) {
     if (c->epsilon == 0) return argmax_tiebreak(uct, n, g, err);
-    double u = (double)u32_to_unit(rng_next(g));
-    if (u < c->epsilon) return u32_to_index(rng_next(g), n);
+    double u = rng_random(g);
+    if (u < c->epsilon) return rng_below(g, n);
     return argmax_tiebreak(uct, n, g, err);
 }
 
@@ -829,7 +889,9 @@ static void* worker(void* arg) {
         if (b0 >= J->B) break;
         int64_t b1 = b0 + 16 < J->B ? b0 + 16 : J->B;
         for (int64_t b = b0; b < b1; ++b) {
-            rng_t g = {cfg->seed, J->tree_id0 + b, 0, 0};
+            rng_t g;
+            g.seed = cfg->seed; g.tree = J->tree_id0 + b; g.draws = 0; g.pw = 0; g.mt_mode = cfg->rng_mode == 1; g.mti = 624;
+            if (g.mt_mode) mt_seed(&g, cfg->seed + (uint64_t)(J->tree_id0 + b));
             int e;
             if (cfg->variant == AZO_DISCRETE) {
                 e = search_discrete_one(cfg, J->net, J->tapes, b, J->root_state + b * 4, J->root_n_init ? J->root_n_init[b] : 0, &dt, &g, J->ctr);

@@ -77,8 +77,11 @@ typedef struct {
     float action_bound, log_std_min, log_std_max;
     uint64_t seed;         /* Philox key */
     int32_t eval_mode;     /* AZO_EVAL_* */
-    int32_t reserved_;
+    int32_t rng_mode;      /* 0: Philox streams (default); 1 (AZO_RNG_MT19937, discrete search only): CPython's generator, seeded
+                              with seed + global tree id at the start of every search (azg_oracle.c "AZO_RNG_MT19937") */
 } azo_config;
+#define AZO_RNG_PHILOX 0
+#define AZO_RNG_MT19937 1
 
 /* AZO_EVAL_Q8 contract (the arithmetic the tcgen05 kind::i8 kernel performs; every step is exact integer
  * arithmetic or one correctly rounded IEEE f32 operation, so CPU and GPU agree bit for bit):

@@ -20,6 +20,7 @@ DISCRETE, CONTINUOUS = 0, 1
 ACT_RELU, ACT_ELU = 0, 1
 MATH_LIBM, MATH_DET = 0, 1
 EVAL_FP32, EVAL_Q8 = 0, 1
+RNG_PHILOX, RNG_MT19937 = 0, 1
 VT = {"off_policy": 0, "on_policy": 1, "greedy": 2}
 
 
@@ -38,7 +39,7 @@ class _Cfg(C.Structure):
         ("math_mode", C.c_int32), ("v_target", C.c_int32), ("puct_f32", C.c_int32), ("use_eval_tape", C.c_int32),
         ("c_uct", C.c_double), ("gamma", C.c_double), ("epsilon", C.c_double), ("c_pw", C.c_double), ("kappa", C.c_double),
         ("action_bound", C.c_float), ("log_std_min", C.c_float), ("log_std_max", C.c_float),
-        ("seed", C.c_uint64), ("eval_mode", C.c_int32), ("reserved_", C.c_int32),
+        ("seed", C.c_uint64), ("eval_mode", C.c_int32), ("rng_mode", C.c_int32),
     ]
 
 
@@ -129,12 +130,13 @@ class Config:
     log_std_max: float = 2.0
     seed: int = 34
     eval_mode: int = 0  # EVAL_FP32 | EVAL_Q8
+    rng_mode: int = 0   # RNG_PHILOX | RNG_MT19937 (discrete search: CPython's generator, seeded with seed + tree id per search)
 
     def c(self) -> _Cfg:
         return _Cfg(self.variant, self.n_rollouts, self.num_actions, self.num_components, self.state_dim, self.hidden,
                     self.n_hidden, self.activation, self.math_mode, VT[self.V_target_policy], self.puct_f32,
                     self.use_eval_tape, self.c_uct, self.gamma, self.epsilon, self.c_pw, self.kappa,
-                    self.action_bound, self.log_std_min, self.log_std_max, self.seed, self.eval_mode, 0)
+                    self.action_bound, self.log_std_min, self.log_std_max, self.seed, self.eval_mode, self.rng_mode)
 
     @property
     def rows(self) -> int:

@@ -57,6 +57,20 @@ CASES = {
 }
 
 
+def _mt(cfg: azo.Config) -> azo.Config:
+    cfg.rng_mode = azo.RNG_MT19937
+    return cfg
+
+
+# the discrete search of the reference with its STOCK random module (no shim), seeded random.seed(seed + tree)
+MT_CASES = {
+    "cartpole_mt_n8_eps01": dict(cfg=_mt(azo.discrete_config(n_rollouts=8, epsilon=0.1)), B=16),
+    "cartpole_mt_n50_eps0": dict(cfg=_mt(azo.discrete_config(n_rollouts=50, epsilon=0.0)), B=12),
+    "cartpole_mt_n200_terminal": dict(cfg=_mt(azo.discrete_config(n_rollouts=200, epsilon=0.1)), B=6, roots="tilted"),
+}
+CASES_ALL = dict(CASES, **MT_CASES)
+
+
 def roots_for(case) -> np.ndarray:
     cfg, B = case["cfg"], case["B"]
     if cfg.variant == azo.DISCRETE:
@@ -69,7 +83,7 @@ def roots_for(case) -> np.ndarray:
 
 
 def generate(name: str) -> str:
-    case = CASES[name]
+    case = CASES_ALL[name]
     cfg: azo.Config = case["cfg"]
     cfg.math_mode = azo.MATH_LIBM
     model = RH.make_model(cfg, weight_seed=34)
@@ -99,7 +113,7 @@ def load(name: str):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CASES)
+    names = sys.argv[1:] or list(CASES_ALL)
     for n in names:
         p = generate(n)
         print(n, "->", p, os.path.getsize(p), "bytes")

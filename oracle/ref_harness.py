@@ -161,6 +161,24 @@ class PhiloxRandom:
         return a + ((self._u32() * (b - a + 1)) >> 32)
 
 
+class StockRandom(__import__("random").Random):
+    """CPython's own generator, i.e. the UN-SHIMMED reference: `random.Random(s)` runs exactly what the module-level
+    `random.seed(s)` / `random.random` / `random.choice` / `random.randint` run.  The two overrides only count generator outputs
+    (random() takes two, getrandbits(k <= 32) one); defining getrandbits keeps `_randbelow_with_getrandbits`, the stock algorithm."""
+
+    def __init__(self, seed: int):
+        super().__init__(seed)
+        self.draws = 0
+
+    def random(self) -> float:
+        self.draws += 2
+        return super().random()
+
+    def getrandbits(self, k: int) -> int:
+        self.draws += 1
+        return super().getrandbits(k)
+
+
 class NoiseInjector:
     """Wraps torch.multinomial / torch.normal (stream 1): one index per sample_action call."""
 
@@ -225,7 +243,8 @@ def run_discrete(cfg: azo.Config, model, root_states: np.ndarray, tree_id0: int 
     import alphazero.helpers as H  # type: ignore
     orig_expansion = M.MCTS.expansion
     for b in range(B):
-        rng = PhiloxRandom(cfg.seed, tree_id0 + b)
+        # rng_mode MT19937: the stock generator seeded like `random.seed(seed + tree)` right before the search
+        rng = StockRandom(cfg.seed + tree_id0 + b) if cfg.rng_mode == azo.RNG_MT19937 else PhiloxRandom(cfg.seed, tree_id0 + b)
         H.random = M.random = rng
         counter = [0]
 

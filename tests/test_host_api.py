@@ -131,3 +131,25 @@ def test_stable_normalizer_and_shard_range():
         assert spans[0][0] == 0 and spans[-1][1] == total
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_hydra_yaml_drop_ins_instantiate():
+    """config/mcts/*.yaml = the reference's files with the engine classes as `_target_`: same keys, and
+    `hydra.utils.instantiate(cfg, model=nn)` (agents.py:82) -- resolved here by hand, hydra is not installed -- builds the search
+    objects without touching the GPU (the engine is created at the first search)."""
+    import importlib
+    import os
+    import yaml
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref_keys = {"MCTSDiscrete": {"_target_", "num_actions", "n_rollouts", "gamma", "c_uct", "epsilon", "V_target_policy", "device", "root_state"},
+                "MCTSContinuous": {"_target_", "n_rollouts", "c_pw", "kappa", "gamma", "c_uct", "epsilon", "V_target_policy", "device", "root_state"}}
+    for name, keys in ref_keys.items():
+        with open(os.path.join(root, "config", "mcts", name + ".yaml")) as f:
+            cfg = yaml.safe_load(f)
+        assert set(cfg) == keys  # the keys of /root/reference/config/mcts/<name>.yaml
+        cfg = {k: (2 if v == "${policy.num_actions}" else "cuda:0" if v == "${device}" else v) for k, v in cfg.items()}
+        mod, cls = cfg.pop("_target_").rsplit(".", 1)
+        model = (PolicyNet(4, 128, 2, 2, "relu", num_actions=2) if name == "MCTSDiscrete"
+                 else PolicyNet(3, 128, 3, 6, "elu", num_components=2, action_bound=2.0))
+        obj = getattr(importlib.import_module(mod), cls)(model=model, **cfg)
+        assert obj.n_rollouts == cfg["n_rollouts"] and obj.c_uct == cfg["c_uct"] and obj.gamma == cfg["gamma"]

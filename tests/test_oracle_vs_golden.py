@@ -85,3 +85,23 @@ def test_tree_id_offset_is_batch_invariant():
     part = azo.search(cfg, g["weights"], g["root_state"][5:9], tree_id0=5)
     for k in ("counts", "Q", "eW", "parent", "action"):
         assert np.array_equal(full[k][5:9], part[k]), k
+
+
+MT_CASES = sorted(G.MT_CASES)
+
+
+@pytest.mark.parametrize("name", MT_CASES)
+def test_mt19937_mode_reproduces_the_unshimmed_reference(name):
+    """with rng_mode = MT19937 the selection draws are CPython's (init_by_array seeding, 53-bit random(),
+    _randbelow_with_getrandbits for choice / randint), so the goldens of the reference run with its STOCK `random` module --
+    `random.Random(seed + tree)`, no shim -- are reproduced: level A (tapes) bit for bit including the number of generator
+    outputs consumed, level B (own MLP) with exact integers."""
+    cfg, g = G.load(name)
+    assert cfg.rng_mode == azo.RNG_MT19937
+    cfg.use_eval_tape, cfg.math_mode = 1, azo.MATH_LIBM
+    o = azo.search(cfg, None, g["root_state"], g.get("root_n_init"), tapes=_tapes(cfg, g))
+    assert_tree_equal(o, g, True, exact_fp=True, skip=("head",))
+    assert o["counters"][5] == g["draws"].sum(), "number of MT19937 outputs consumed differs"
+    cfg.use_eval_tape, cfg.math_mode = 0, azo.MATH_DET
+    o = azo.search(cfg, g["weights"], g["root_state"], g.get("root_n_init"))
+    assert_tree_equal(o, g, True, exact_fp=False)
