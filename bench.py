@@ -197,10 +197,29 @@ def run_reference(args, variant, B, N, rank, world):
                        "note": "CPU C port (oracle/azg_oracle.c) of the reference's python search; the python reference cannot travel"},
             "cpu_baseline": {"value": v, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: keep a private handle on the real stdout for it and point file descriptor 1 at
+    stderr, so that whatever a library prints there (NCCL's version banner under NCCL_DEBUG=VERSION, which ignores NCCL_DEBUG_FILE)
+    ends up on stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -449,7 +468,7 @@ def main():
             "counters_per_sim": {k: pc[k] / max(1, pc["sims"]) for k in ("levels", "children_scanned", "pw_inserts", "evals")},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
