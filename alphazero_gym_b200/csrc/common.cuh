@@ -7,8 +7,8 @@
 //     only: 64 B for the discrete tree (node + its A=2 edges) and 64 B for the continuous tree (sector 0:
 //     edge statistics + the child node it leads to -- edges and non-root nodes are 1:1, SURVEY 7-4;
 //     sector 1: that node's inline child list).  64 B is also the DRAM burst, so a row miss wastes nothing;
-//   * the continuous tree adds a 64 B control block per tree (scalars, inline path, root child map) and a
-//     compact root edge table (the root's children statistics, 32 B each, contiguous);
+//   * the continuous tree adds a 64 B control block per tree (scalars, inline path, root child map) and a root edge table (the
+//     root's children statistics, 32 B each), both TREE-INTERLEAVED ([4][trees] chunk planes / [16][trees], see TreeParams);
 //   * COLD structure-of-arrays side tables that select/backup never touch: CartPole env state, cached policy head.
 #pragma once
 #include <cuda_runtime.h>

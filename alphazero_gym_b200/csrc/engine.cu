@@ -2,8 +2,9 @@
 //
 // One search = init -> evaluate(root) -> [continuous: root widening insert] ->
 //              N x { step<backup of previous sim, select, expand> -> evaluate(leaves) } -> final backup.
-// Trees are independent, so there is no inter-CTA synchronisation anywhere; the 2N+3 launches of a search
-// are captured once into a CUDA graph per (B, n_rollouts, tape, tree_id0) and replayed.
+// Trees are independent, so there is no inter-CTA synchronisation anywhere.  Two schedules, identical results: the whole search as
+// ONE persistent kernel per chunk of trees (AZG_FLAG_FUSED, qmlp2.cuh: default with the tensor-core evaluation), or 2N+3 launches
+// captured once into a CUDA graph per (B, n_rollouts, tape, tree_id0) and replayed.
 #include <cuda_runtime.h>
 
 #include <cmath>

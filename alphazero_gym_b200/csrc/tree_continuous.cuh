@@ -12,13 +12,14 @@
 // same work costs ~1/10 of the issue slots, the f64 env step / Box-Muller run on full warps with no
 // barriers, and memory-level parallelism comes from 65536 independent threads instead of from lanes.
 //
-// Memory traffic is what bounds this kernel (profiles/r1b: 128 MB of DRAM traffic per launch against 19 MB
-// algorithmic), so the layout is built around 64 B DRAM bursts:
-//   * one 64 B control block per tree (CCtl) carries every scalar, the recorded path and the root's child map;
-//   * the root is scanned in every simulation and has the widest fan-out, so the statistics sectors of its
-//     children sit contiguously in the root edge table (2 children per 64 B burst instead of 1);
-//   * a node's hidden env state rides in the second sector of its row together with its child list, so
-//     entering a node and expanding below it cost no extra line.
+// What bounds the step (profiles/README.md r1f): a chain of dependent loads per tree (17 us floor at any batch size)
+// plus, beyond ~200 trees per SM, the L1 tag lookups of per-thread scattered accesses -- not HBM bandwidth.  Hence the layout:
+//   * one 64 B control block per tree (CCtl: every scalar, the recorded path, the root's child map) stored as four 16-byte chunk
+//     planes [4][trees], and the root edge table (the statistics sectors of the root's children: the root is scanned in every
+//     simulation and has the widest fan-out) as [16][trees]: a warp's 32 consecutive trees touch 4 / 8 lines per access, not 32;
+//   * W, n and the child node's n in the first 16 bytes of a hot sector: one load per scanned child, one store per backup level;
+//   * a node's hidden env state rides in the second sector of its row together with its child list, so entering a node and
+//     expanding below it cost no extra line.
 #pragma once
 #include "common.cuh"
 #include "env.cuh"
