@@ -30,7 +30,7 @@
 #define Q2_EPI_THREADS 512
 #define Q2_THREADS 768                // 16 epilogue warps + the MMA warpgroup + the post-processing warpgroup (registers rebalanced with setmaxnreg)
 #define Q2_MAX_TILES 16               // whole-search kernel: tiles per CTA and launch (engine.cu cuts larger batches into chunks)
-#define Q2_BAR_PHASE 6                // named barrier of the whole-search kernel: 16 epilogue warps + the post-processing warpgroup
+#define Q2_PHASE_THREADS 640           // whole-search kernel: the threads that meet between phases (16 epilogue warps + the post-processing warpgroup)
 #define Q2_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24))  // s8 x s8 -> s32, K-major, N = 64, M = 128
 #define Q2_ACC_COLS 192               // accumulator window of a tile: PA | PB | PC, 64 columns each
 #define Q2_SCRATCH_COL 384            // head partial sums of tile T: columns 384 + 64 T + 16 cq + c
@@ -86,6 +86,15 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Phase boundary of the whole-search kernel: every participant arrives (release) and waits for the phase to complete (acquire), so
+// the global-memory writes of one phase (tree tables, X) are visible to the readers of the next.  An mbarrier like every other
+// cross-role synchronisation of this kernel (a 640-thread named barrier next to the MMA warpgroup parked at barrier 0 computes the
+// same results but is reported by compute-sanitizer's synccheck).
+__device__ __forceinline__ void phase_sync(uint64_t* bar, uint32_t& parity) {
+    mbar_arrive(bar);
+    mbar_wait(bar, parity);
+    parity ^= 1u;
 }
 
 // per-CTA constants of the epilogue warps
@@ -211,7 +220,7 @@ __device__ __forceinline__ void q2_finish_tile(const MlpParams& p, uint32_t tb, 
 //   Trees never interact, so nothing needs a grid-wide barrier between simulations: a CTA owns its trees for the whole search
 //   and alternates two phases, n_sims + 1 times: (1) the evaluation of all its tiles, exactly as above; (2) a TREE PHASE in which
 //   the 16 epilogue warps run one thread per tree: backup of the finished simulation, descent + expansion of the next (c_step,
-//   tree_continuous.cuh -- the body of k_step_continuous), next network input into X.  Two 640-thread named barriers separate the
+//   tree_continuous.cuh -- the body of k_step_continuous), next network input into X.  Two phase boundaries (an mbarrier all 640 of them arrive at and wait on) separate the
 //   phases (epilogue warps + post-processing warpgroup; the MMA warp only follows its mbarriers).  What this buys over one launch
 //   per kernel and simulation: weights, TMEM and barriers are set up once per search instead of once per simulation (~10 us of
 //   ramp per evaluation launch, tools/step_scaling.py), no launch gaps, and the 148 CTAs drift out of phase, so the tree phases
@@ -223,7 +232,7 @@ template <int S, int ACT, int NL, bool FUSED>
 __global__ void __launch_bounds__(Q2_THREADS, 1)
 k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chunk_begin, const int chunk_end) {
     extern __shared__ __align__(1024) uint8_t qsm_raw[];
-    __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2], hfull[2], hfree[2];
+    __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2], hfull[2], hfree[2], phase_bar;
     __shared__ uint32_t tmem_base_s;
     // round up to 1024 B with an OFFSET on the shared pointer: a round trip through uintptr_t loses the address space and every
     // access below becomes a generic LD/ST (long-scoreboard latency) instead of LDS/STS
@@ -254,6 +263,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
 
     if (tid == 0) {
         mbar_init(&wbar, 1);
+        mbar_init(&phase_bar, Q2_PHASE_THREADS);
         for (int T = 0; T < 2; ++T) {
             mbar_init(&full[T], 1);
             mbar_init(&ready[T], Q2_EPI_THREADS);
@@ -293,7 +303,8 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         const float* bh = fl + S * 128 + 128 + NL * 2 * 128 + 128 * p.PO_PAD;
         uint32_t hph = 0, nev = 0;
         int ev_row = 0;
-        if (FUSED) group_sync(Q2_BAR_PHASE, 640);  // the roots are initialised (c_init)
+        uint32_t pph = 0;  // parity of the next phase boundary
+        if (FUSED) phase_sync(&phase_bar, pph);  // the roots are initialised (c_init)
 #pragma unroll 1
         for (int s = 0; s < n_evals; ++s) {
 #pragma unroll 1
@@ -322,8 +333,8 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
             else mbar_arrive(&hfree[T]);
         }
         if (FUSED) {
-            group_sync(Q2_BAR_PHASE, 640);  // every row of this evaluation is finished: the tree phase may start
-            group_sync(Q2_BAR_PHASE, 640);  // the tree phase is over: leaf words and X of the next simulation are in place
+            phase_sync(&phase_bar, pph);  // every row of this evaluation is finished: the tree phase may start
+            phase_sync(&phase_bar, pph);  // the tree phase is over: leaf words and X of the next simulation are in place
         }
         }
         if (nev && p.mode == 0) p.evals[ev_row] += nev;  // only the total over trees is reported (azg_get_counters)
@@ -383,12 +394,13 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         long long cyc_tree = 0, cyc_sync = 0;
         const long long cyc_begin = clock64();
         const Tabs tabs = {s_pw, s_rcp, s_sq, FUSED_TAB};
+        uint32_t pph = 0;  // parity of the next phase boundary
         if (FUSED) {  // MCTSContinuous.initialize_search for every tree of the CTA
             for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
                 if (S == 4) d_init(tp, row_begin + i);  // state_dim 4 = CartPole = the discrete tree (engine.cu checks it)
                 else c_init(tp, row_begin + i);
             }
-            group_sync(Q2_BAR_PHASE, 640);
+            phase_sync(&phase_bar, pph);
         }
         uint32_t fullph = 0;  // bit T: parity of the next wait on full[T]
         uint32_t hfph = 0;    // bit T: parity of the next wait on hfree[T]
@@ -476,7 +488,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         if (FUSED) {
             // ---- tree phase: one thread per tree of the CTA
             const long long c0 = clock64();
-            group_sync(Q2_BAR_PHASE, 640);  // the post-processing warps have finished every row of this evaluation
+            phase_sync(&phase_bar, pph);  // the post-processing warps have finished every row of this evaluation
             const long long c1 = clock64();
 #pragma unroll 1
             for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
@@ -488,7 +500,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
                     c_step(tp, tabs, gr, s > 0, s + 1 < n_evals);     // backup of simulation s, descent + expansion of simulation s + 1
                 }
             }
-            group_sync(Q2_BAR_PHASE, 640);
+            phase_sync(&phase_bar, pph);
             cyc_sync += c1 - c0;
             cyc_tree += clock64() - c1;
         }
