@@ -25,7 +25,7 @@ EXPORTS = [
     "azg_search_discrete", "azg_search_continuous", "azg_cmax", "azg_root_results", "azg_search_host", "azg_status",
     "azg_rows", "azg_set_tapes", "azg_dump_tree_discrete", "azg_dump_tree_continuous", "azg_get_counters",
     "azg_head_dim", "azg_mlp_forward", "azg_env_step", "azg_profile_search", "azg_set_seed", "azg_selfplay_seed",
-    "azg_selfplay_step", "azg_fused_stats",
+    "azg_selfplay_step", "azg_fused_stats", "azg_search_host_begin", "azg_search_host_end",
 ]
 
 
@@ -88,6 +88,9 @@ def load():
     L.azg_root_results.restype, L.azg_root_results.argtypes = C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]
     L.azg_search_host.restype = C.c_int
     L.azg_search_host.argtypes = [vp, i32, vp, vp, i32, i64, vp, vp, vp, vp, vp]
+    L.azg_search_host_begin.restype = C.c_int
+    L.azg_search_host_begin.argtypes = [vp, i32, i32, vp, vp, i32, i64, vp, vp, vp, vp, vp]
+    L.azg_search_host_end.restype, L.azg_search_host_end.argtypes = C.c_int, [vp, i32]
     L.azg_status.restype, L.azg_status.argtypes = C.c_int, [vp, vp]
     L.azg_rows.restype, L.azg_rows.argtypes = i32, [vp]
     L.azg_set_tapes.restype, L.azg_set_tapes.argtypes = C.c_int, [vp, vp, vp, vp]

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <map>
 #include <string>
 #include <tuple>
@@ -90,6 +91,17 @@ struct azg_engine {
     int32_t* r_nchild = nullptr;
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;
+    // azg_search_host_begin / _end: a second set of result buffers, a copy stream and per-slot events, so that the D2H of one search's
+    // results overlaps the next search
+    float* r2_actions = nullptr;
+    int32_t* r2_counts = nullptr;
+    double* r2_Q = nullptr;
+    double* r2_Vt = nullptr;
+    int32_t* r2_nchild = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    int32_t* h_err = nullptr;  // pinned, one word per slot
+    bool pending[2] = {false, false};
     cudaStream_t own_stream = nullptr;
     // tapes
     const float *tapeV = nullptr, *tapeP = nullptr, *tapeA = nullptr;
@@ -127,6 +139,14 @@ extern "C" void azg_destroy(azg_engine* e) {
     for (void* q : ptrs)
         if (q) cudaFree(q);
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    if (e->h_err) cudaFreeHost(e->h_err);
+    for (void* q : {(void*)e->r2_actions, (void*)e->r2_counts, (void*)e->r2_Q, (void*)e->r2_Vt, (void*)e->r2_nchild})
+        if (q) cudaFree(q);
+    for (int k = 0; k < 2; ++k) {
+        if (e->ev_done[k]) cudaEventDestroy(e->ev_done[k]);
+        if (e->ev_copied[k]) cudaEventDestroy(e->ev_copied[k]);
+    }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -816,6 +836,84 @@ extern "C" int azg_search_host(azg_engine* e, int32_t B, const double* h_root_st
         memcpy(h_n_children, p_nc, (size_t)B * sizeof(int32_t));
     }
     return rc;
+}
+
+// Pipelined form of azg_search_host: begin(slot) enqueues H2D of the roots, the search, the result extraction and -- on a copy stream --
+// the D2H of the results, and returns at once; end(slot) waits until that slot's results are in the caller's buffers.  With two slots
+// in flight the PCIe transfer of search i (13 MB at 65536 trees) runs under search i + 1.  Every host buffer must be page-locked.
+extern "C" int azg_search_host_begin(azg_engine* e, int32_t slot, int32_t B, const double* h_root_state, const int32_t* h_root_n_init,
+                                     int32_t n_rollouts, int64_t tree_id0, float* h_actions, int32_t* h_counts, double* h_Q,
+                                     double* h_V_target, int32_t* h_n_children) {
+    if (!e || !h_root_state || !h_actions || !h_counts || !h_Q || !h_V_target || !h_n_children) return fail(AZG_EINVAL, "null argument");
+    if (slot < 0 || slot > 1) return fail(AZG_EINVAL, "slot must be 0 or 1");
+    if (B < 1 || B > e->cfg.max_trees) return fail(AZG_EINVAL, "B out of range");
+    if (e->cfg.variant == AZG_CONTINUOUS && h_root_n_init) return fail(AZG_EINVAL, "root_n_init is a discrete-only argument");
+    if (e->pending[slot]) return fail(AZG_EINVAL, "slot is still in flight: call azg_search_host_end first");
+    CK(cudaSetDevice(e->cfg.device));
+    auto pinned = [](const void* h) {
+        cudaPointerAttributes at;
+        const bool ok = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return ok;
+    };
+    if (!(pinned(h_root_state) && pinned(h_actions) && pinned(h_counts) && pinned(h_Q) && pinned(h_V_target) && pinned(h_n_children) &&
+          (!h_root_n_init || pinned(h_root_n_init))))
+        return fail(AZG_EINVAL, "azg_search_host_begin needs page-locked host buffers (cudaHostAlloc / cudaHostRegister / pin_memory)");
+    const size_t cm = e->cmax, Bm = e->cfg.max_trees;
+    if (!e->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming));
+        }
+        CK(cudaMallocHost(&e->h_err, 2 * sizeof(int32_t)));
+        CK(cudaMalloc(&e->r2_actions, Bm * cm * sizeof(float)));
+        CK(cudaMalloc(&e->r2_counts, Bm * cm * sizeof(int32_t)));
+        CK(cudaMalloc(&e->r2_Q, Bm * cm * sizeof(double)));
+        CK(cudaMalloc(&e->r2_Vt, Bm * sizeof(double)));
+        CK(cudaMalloc(&e->r2_nchild, Bm * sizeof(int32_t)));
+    }
+    float* ra = slot ? e->r2_actions : e->r_actions;
+    int32_t* rc_ = slot ? e->r2_counts : e->r_counts;
+    double* rq = slot ? e->r2_Q : e->r_Q;
+    double* rv = slot ? e->r2_Vt : e->r_Vt;
+    int32_t* rn = slot ? e->r2_nchild : e->r_nchild;
+    cudaStream_t st = e->own_stream;
+    const int sd = e->cfg.variant == AZG_DISCRETE ? 4 : 2;
+    CK(cudaMemcpyAsync(e->root_state, h_root_state, (size_t)B * sd * sizeof(double), cudaMemcpyHostToDevice, st));
+    const int32_t* d_rn = nullptr;
+    if (h_root_n_init) {
+        CK(cudaMemcpyAsync(e->root_n_init, h_root_n_init, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        d_rn = e->root_n_init;
+    }
+    int rc = run_search(e, B, e->root_state, d_rn, n_rollouts, tree_id0, st);
+    if (rc) return rc;
+    rc = azg_root_results(e, B, ra, rc_, rq, rv, rn, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(e->h_err + slot, e->err, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(e->err, 0, sizeof(int32_t), st));
+    CK(cudaEventRecord(e->ev_done[slot], st));
+    CK(cudaStreamWaitEvent(e->copy_stream, e->ev_done[slot], 0));
+    CK(cudaMemcpyAsync(h_actions, ra, (size_t)B * cm * sizeof(float), cudaMemcpyDeviceToHost, e->copy_stream));
+    CK(cudaMemcpyAsync(h_counts, rc_, (size_t)B * cm * sizeof(int32_t), cudaMemcpyDeviceToHost, e->copy_stream));
+    CK(cudaMemcpyAsync(h_Q, rq, (size_t)B * cm * sizeof(double), cudaMemcpyDeviceToHost, e->copy_stream));
+    CK(cudaMemcpyAsync(h_V_target, rv, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, e->copy_stream));
+    CK(cudaMemcpyAsync(h_n_children, rn, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, e->copy_stream));
+    CK(cudaEventRecord(e->ev_copied[slot], e->copy_stream));
+    e->pending[slot] = true;
+    return AZG_OK;
+}
+
+extern "C" int azg_search_host_end(azg_engine* e, int32_t slot) {
+    if (!e || slot < 0 || slot > 1) return fail(AZG_EINVAL, "bad argument");
+    if (!e->pending[slot]) return fail(AZG_EINVAL, "nothing in flight in this slot");
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaEventSynchronize(e->ev_copied[slot]));
+    e->pending[slot] = false;
+    const int32_t h = e->h_err[slot];
+    if (h & ERR_NAN) return fail(AZG_ENAN, "NaN in a UCT vector (helpers.py:47-48)");
+    if (h & ERR_CAPACITY) return fail(AZG_ECAPACITY, "tree arena or child fan-out capacity exceeded");
+    return AZG_OK;
 }
 
 // host copies of the tree-interleaved tables, back in per-tree order: ctl[t], et[t * 16 + j]

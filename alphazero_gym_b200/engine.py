@@ -195,6 +195,21 @@ class SearchEngine:
         self.last_B = B
         return out
 
+    def search_host_begin(self, slot: int, root_state: np.ndarray, n_rollouts: int, out: Dict[str, np.ndarray],
+                          root_n_init: Optional[np.ndarray] = None, tree_id0: int = 0) -> None:
+        """Pipelined search_host (azg_search_host_begin): returns at once; `root_state`, `root_n_init` and the `out` buffers
+        (host_buffers) must be page-locked and stay untouched until search_host_end(slot)."""
+        B = root_state.shape[0]
+        assert root_state.dtype == np.float64 and root_state.flags.c_contiguous and out["actions"].shape == (B, self.cmax)
+        check(self._lib.azg_search_host_begin(self._h, slot, B, _ptr(root_state), _ptr(root_n_init), n_rollouts, tree_id0,
+                                              _ptr(out["actions"]), _ptr(out["counts"]), _ptr(out["Q"]), _ptr(out["V_target"]),
+                                              _ptr(out["n_children"])))
+        self.last_B = B
+
+    def search_host_end(self, slot: int) -> None:
+        """Blocks until the results of `slot` are in its host buffers (azg_search_host_end)."""
+        check(self._lib.azg_search_host_end(self._h, slot))
+
     # ---- parity hooks ----------------------------------------------------------------------------------
     def set_tapes(self, V: Optional[np.ndarray], prior: Optional[np.ndarray] = None,
                   action: Optional[np.ndarray] = None) -> None:

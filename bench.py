@@ -310,6 +310,20 @@ def main():
         def host_step(i):
             return eng.search_host(roots_pinned, N, tree_id0=tree_id0, out=host_out)
 
+        host_out2 = eng.host_buffers(B)
+
+        def host_pipeline(steps):
+            """The same K searches through the pipelined entry points (azg_search_host_begin / _end, two slots in flight): every
+            step still copies its roots in from pinned host memory and its results out; the D2H of step i runs under step i + 1."""
+            outs = (host_out, host_out2)
+            for i in range(steps):
+                if i >= 2:
+                    eng.search_host_end(i & 1)
+                eng.search_host_begin(i & 1, roots_pinned, N, outs[i & 1], tree_id0=tree_id0)
+            for i in range(max(0, steps - 2), steps):
+                eng.search_host_end(i & 1)
+            return outs[(steps - 1) & 1]
+
         h2d = roots_h.nbytes
         extra_launches = 1  # the root-results kernel
 
@@ -340,6 +354,15 @@ def main():
         out = host_step(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_blocking_s = None
+    if not selfplay:  # the pipelined entry points: the number reported as e2e; the blocking call's stays next to it
+        host_pipeline(2)
+        barrier()
+        t0 = time.perf_counter()
+        out = host_pipeline(args.steps)
+        e2e_blocking_s, e2e_s = e2e_s, time.perf_counter() - t0
+        api = ("azg_search_host_begin / azg_search_host_end via SearchEngine.search_host_begin / _end, two searches in flight, page-locked "
+               "host buffers (wall clock from the first begin to the last end); blocking_value = azg_search_host, one call per step")
     clk = clocks.stop()
     checksum = int(drv.t["counts"].sum()) if selfplay else int(out["counts"].sum())
     assert checksum == B * N, f"visit counts do not add up: {checksum} != {B * N}"
@@ -439,10 +462,10 @@ def main():
         cpu = {"value": v, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample}
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, e2e_s * 1e3, (e2e_blocking_s or 0.0) * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    ms_max, e2e_ms_max, e2e_blocking_ms_max = float(t[0]), float(t[1]), float(t[2])
     total_sims = world * B * N * args.steps
     if rank == 0:
         line = {
@@ -457,7 +480,8 @@ def main():
                        "l2": "node tables per GPU (%.0f MB) exceed the 126 MB L2; no explicit flush" % (eng.rows * B * (32 + 16 + 32) / 1e6)
                        if variant == "continuous" else "tables are L2-resident at this size (SURVEY 8d config 3); no explicit flush"},
             "e2e": {"value": total_sims / (e2e_ms_max * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_max / args.steps, "api": api},
+                    "ms_per_step": e2e_ms_max / args.steps, "api": api,
+                    **({"blocking_value": total_sims / (e2e_blocking_ms_max * 1e-3)} if e2e_blocking_ms_max > 0 else {})},
             "gpu_launches": launches_per_step * args.steps,
             **({"selfplay": {"max_episode_length": 200, "weight_broadcast_every_steps": SELFPLAY_BROADCAST_EVERY,
                              "collectives_per_step": "all_gather of 5 replay-row tensors (C2); broadcast of the flat weights every k steps (C1)",

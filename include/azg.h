@@ -117,6 +117,15 @@ int azg_search_host(azg_engine* e, int32_t B, const double* h_root_state, const 
                     int64_t tree_id0, float* h_actions, int32_t* h_counts, double* h_Q, double* h_V_target,
                     int32_t* h_n_children);
 
+/* The same, pipelined: begin(slot) enqueues everything -- H2D of the roots, the search, result extraction and, on a copy stream, the D2H
+ * of the results -- and returns at once; end(slot) blocks until that slot's results are in the caller's buffers and returns the search's
+ * status.  Two slots (0, 1): with both in flight the PCIe transfer of one search's results runs under the next search.  All host
+ * buffers must be page-locked and must stay untouched until end(slot). */
+int azg_search_host_begin(azg_engine* e, int32_t slot, int32_t B, const double* h_root_state, const int32_t* h_root_n_init,
+                          int32_t n_rollouts, int64_t tree_id0, float* h_actions, int32_t* h_counts, double* h_Q, double* h_V_target,
+                          int32_t* h_n_children);
+int azg_search_host_end(azg_engine* e, int32_t slot);
+
 /* Device status of the last search(es): AZG_OK, AZG_ENAN or AZG_ECAPACITY.  Synchronises `stream`. */
 int azg_status(azg_engine* e, void* stream);
 

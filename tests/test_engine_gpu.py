@@ -210,3 +210,44 @@ def test_host_entry_point_with_page_locked_buffers():
             assert np.array_equal(a[k], b[k]), k
     finally:
         eng.close()
+
+
+@pytest.mark.gpu
+def test_pipelined_host_entry_points_equal_the_blocking_call():
+    """azg_search_host_begin / _end with two searches in flight return what azg_search_host returns, slot by slot, and refuse
+    pageable buffers and a slot that is still in flight."""
+    import torch
+    import enginelib as E
+    from alphazero_gym_b200._cabi import AzgError
+    cfg = azo.continuous_config(n_rollouts=25)
+    cfg.eval_mode = azo.EVAL_Q8
+    B = 700
+    w = (np.random.default_rng(4).standard_normal(cfg.num_weights) * 0.08).astype(np.float32)
+    eng = E.SearchEngine(E.engine_config(cfg, B))
+    try:
+        eng.set_weights(w)
+        roots = [torch.from_numpy(G.pendulum_roots(B, seed=s)).pin_memory().numpy() for s in (1, 2, 3)]
+        want = [{k: v.copy() for k, v in eng.search_host(r, cfg.n_rollouts, tree_id0=9).items()} for r in roots]
+        outs = [eng.host_buffers(B), eng.host_buffers(B)]
+        eng.search_host_begin(0, roots[0], cfg.n_rollouts, outs[0], tree_id0=9)
+        eng.search_host_begin(1, roots[1], cfg.n_rollouts, outs[1], tree_id0=9)
+        with pytest.raises(AzgError):
+            eng.search_host_begin(1, roots[2], cfg.n_rollouts, outs[1], tree_id0=9)  # slot 1 is in flight
+        eng.search_host_end(0)
+        for k in want[0]:
+            assert np.array_equal(outs[0][k], want[0][k]), k
+        eng.search_host_begin(0, roots[2], cfg.n_rollouts, outs[0], tree_id0=9)
+        eng.search_host_end(1)
+        for k in want[1]:
+            assert np.array_equal(outs[1][k], want[1][k]), k
+        eng.search_host_end(0)
+        for k in want[2]:
+            assert np.array_equal(outs[0][k], want[2][k]), k
+        with pytest.raises(AzgError):
+            eng.search_host_end(0)  # nothing in flight
+        pageable = dict(actions=np.empty((B, eng.cmax), np.float32), counts=np.empty((B, eng.cmax), np.int32),
+                        Q=np.empty((B, eng.cmax), np.float64), V_target=np.empty(B, np.float64), n_children=np.empty(B, np.int32))
+        with pytest.raises(AzgError):
+            eng.search_host_begin(0, roots[0], cfg.n_rollouts, pageable, tree_id0=9)
+    finally:
+        eng.close()
