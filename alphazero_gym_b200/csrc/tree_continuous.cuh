@@ -114,8 +114,58 @@ __device__ __forceinline__ float sample_action(const TreeParams& p, const float*
     return p.action_bound > 0.0f ? __fmul_rn(p.action_bound, det::tanhf_(x)) : x;
 }
 
+// The same for a compile-time K: the head values stay in registers (the run-time-K version indexes two local arrays dynamically,
+// i.e. through local memory, and next to 215 KB of shared memory the whole-search kernel has almost no L1 to catch that: measured
+// 5 us of a 22 us tree phase), and only the normal of the SELECTED component is generated (same value as z[k] above).
+template <int K>
+__device__ __forceinline__ float new_action_k(const TreeParams& p, const float* hptr, int64_t tree, int j) {
+    constexpr int HS = (3 * K + 3) / 4 * 4;
+    float h[HS];
+#pragma unroll
+    for (int i = 0; i < HS / 4; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(hptr)[i];
+        h[4 * i] = v.x; h[4 * i + 1] = v.y; h[4 * i + 2] = v.z; h[4 * i + 3] = v.w;
+    }
+    const uint64_t seed = __ldg(p.seedp);
+    const float u = u32_to_unit(rng_block(seed, tree, 1, j, 0).x);
+    int k = 0;
+    if (K > 1) {
+        float cum = h[2 * K];
+#pragma unroll
+        for (int i = 1; i < K; ++i)
+            if (k == i - 1 && !(u < cum)) {
+                k = i;
+                cum = __fadd_rn(cum, h[2 * K + i]);
+            }
+    }
+    float mu = h[0], sg = h[K];
+#pragma unroll
+    for (int i = 1; i < K; ++i)
+        if (i == k) { mu = h[i]; sg = h[K + i]; }
+    const u32x4 c = rng_block(seed, tree, 1, j, 1 + (k >> 1));
+    const double u1 = ((double)c.x + 0.5) * 2.3283064365386963e-10;
+    const double u2 = ((double)c.y + 0.5) * 2.3283064365386963e-10;
+    const double rad = sqrt(-2.0 * det::log_(u1));
+    double sn, cs;
+    det::sincos_(6.283185307179586 * u2, sn, cs);
+    const float z = (k & 1) ? (float)(rad * sn) : (float)(rad * cs);
+    const float x = __fadd_rn(__fmul_rn(z, sg), mu);
+    return p.action_bound > 0.0f ? __fmul_rn(p.action_bound, det::tanhf_(x)) : x;
+}
+
 __device__ __forceinline__ float new_action(const TreeParams& p, int t, int node, int row, int j) {
     if (p.use_tape) return p.tapeA[(size_t)t * p.R + row];
+    {
+        const float* hptr = p.chead + ((size_t)t * p.R + node) * p.HS;
+        const int64_t tree = p.tree_id0 + t;
+        switch (p.K) {
+            case 1: return new_action_k<1>(p, hptr, tree, j);
+            case 2: return new_action_k<2>(p, hptr, tree, j);
+            case 3: return new_action_k<3>(p, hptr, tree, j);
+            case 4: return new_action_k<4>(p, hptr, tree, j);
+            default: break;
+        }
+    }
     // the node's cached policy head (mu[K], sigma[K], prob[K]; HS = 3K rounded up to 4 floats) in 16-byte loads issued before the noise
     float head[3 * AZG_MAX_K];
     const float4* hp = reinterpret_cast<const float4*>(p.chead + ((size_t)t * p.R + node) * p.HS);
