@@ -163,9 +163,60 @@ __device__ __forceinline__ void softmax_seq(const float* l, int n, float* p) {
     for (int i = 0; i < n; ++i) p[i] = __fdiv_rn(p[i], s);
 }
 
+// mode 0, continuous tree, compile-time K: the same values as the generic path below with every array index static, so that raw[] and
+// post[] live in registers (the run-time-K version goes through local memory; in the whole-search kernel, which has almost no L1, that
+// was 2.3 us per simulation the evaluation warps spent waiting for the post-processing warps at the phase boundary)
+template <int K>
+__device__ __forceinline__ void finish_row_continuous(const MlpParams& p, int gr, int leafw, double lr, float V, const float* raw) {
+    constexpr int NP = 3 * K, HSK = (NP + 3) / 4 * 4;
+    float post[HSK];
+#pragma unroll
+    for (int i = 0; i < HSK; ++i) post[i] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        post[k] = raw[k];
+        float ls = raw[K + k];
+        ls = ls < p.ls_min ? p.ls_min : ls;
+        ls = ls > p.ls_max ? p.ls_max : ls;
+        post[K + k] = det::expf_(ls);
+    }
+    if (K > 1) {  // softmax_seq over the K mixture logits, same operation order
+        float m = raw[2 * K];
+#pragma unroll
+        for (int i = 1; i < K; ++i) m = raw[2 * K + i] > m ? raw[2 * K + i] : m;
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            post[2 * K + i] = det::expf_(__fsub_rn(raw[2 * K + i], m));
+            sum = __fadd_rn(sum, post[2 * K + i]);
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) post[2 * K + i] = __fdiv_rn(post[2 * K + i], sum);
+    } else {
+        post[2] = 1.0f;
+    }
+    const size_t ri = (size_t)gr * p.R + (leafw & LEAF_ROW_MASK);
+    if (leafw & LEAF_TERMINAL) V = 0.0f;  // mcts.py:619-623
+    if (leafw & LEAF_ROOTCHILD) p.et[(size_t)((leafw >> LEAF_J_SHIFT) & 0xFF) * p.BS + gr].V = V;
+    else p.crows[ri].V = V;
+    reinterpret_cast<double*>(p.ctl + (size_t)p.BS + gr)[1] = lr + (double)__fmul_rn(p.gamma_f32, V);  // CCtl::leafR = chunk 1, bytes 8..15
+    float4* h = reinterpret_cast<float4*>(p.chead + ri * p.HS);
+#pragma unroll
+    for (int i = 0; i < HSK / 4; ++i) h[i] = make_float4(post[4 * i], post[4 * i + 1], post[4 * i + 2], post[4 * i + 3]);
+}
+
 // post-processing + write-back of one evaluated row: V and the raw policy-head outputs -> softmax priors / GMM parameters ->
 // the tree tables (mode 0) or dense outputs (mode 1).  Shared by k_mlp and k_qmlp2; the caller counts the evaluation.
 __device__ __forceinline__ void mlp_finish_row(const MlpParams& p, int gr, int leafw, double lr, float V, const float* raw) {
+    if (p.mode == 0 && p.variant == 1) {
+        switch (p.K) {
+            case 1: finish_row_continuous<1>(p, gr, leafw, lr, V, raw); return;
+            case 2: finish_row_continuous<2>(p, gr, leafw, lr, V, raw); return;
+            case 3: finish_row_continuous<3>(p, gr, leafw, lr, V, raw); return;
+            case 4: finish_row_continuous<4>(p, gr, leafw, lr, V, raw); return;
+            default: break;
+        }
+    }
     float post[3 * AZG_MAX_K];
     int npost;
     if (p.variant == 0) {

@@ -194,17 +194,22 @@ __device__ __forceinline__ void q2_finish_tile(const MlpParams& p, uint32_t tb, 
                                                double lr, uint64_t* hfree, uint32_t& nev, int& ev_row) {
     const uint32_t lane_base = tb + ((uint32_t)(lg * 32) << 16) + Q2_SCRATCH_COL + T * 64;
     float out[Q2_MAX_PO];
-#pragma unroll 1
-    for (int c4 = 0; c4 < p.PO_PAD / 4; ++c4) {
-        float q0[4], q1[4], q2[4], q3[4];
-        tmem_ld4f(lane_base + c4 * 4, q0);
-        tmem_ld4f(lane_base + 16 + c4 * 4, q1);
-        tmem_ld4f(lane_base + 32 + c4 * 4, q2);
-        tmem_ld4f(lane_base + 48 + c4 * 4, q3);
-        tmem_wait_ld();
+#pragma unroll  // static indices: out[] stays in registers
+    for (int c4 = 0; c4 < Q2_MAX_PO / 4; ++c4) {
+        if (c4 < p.PO_PAD / 4) {
+            float q0[4], q1[4], q2[4], q3[4];
+            tmem_ld4f(lane_base + c4 * 4, q0);
+            tmem_ld4f(lane_base + 16 + c4 * 4, q1);
+            tmem_ld4f(lane_base + 32 + c4 * 4, q2);
+            tmem_ld4f(lane_base + 48 + c4 * 4, q3);
+            tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            out[c4 * 4 + i] = __fadd_rn(__fadd_rn(__fadd_rn(q0[i], q1[i]), __fadd_rn(q2[i], q3[i])), bh[c4 * 4 + i]);
+            for (int i = 0; i < 4; ++i)
+                out[c4 * 4 + i] = __fadd_rn(__fadd_rn(__fadd_rn(q0[i], q1[i]), __fadd_rn(q2[i], q3[i])), bh[c4 * 4 + i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[c4 * 4 + i] = 0.0f;
+        }
     }
     tc_fence_before();
     mbar_arrive(hfree + T);  // the scratch columns may be reused (half-0 activations of the next tile in this slot)
