@@ -208,6 +208,15 @@ __device__ __forceinline__ void finish_row_continuous(const MlpParams& p, int gr
 // post-processing + write-back of one evaluated row: V and the raw policy-head outputs -> softmax priors / GMM parameters ->
 // the tree tables (mode 0) or dense outputs (mode 1).  Shared by k_mlp and k_qmlp2; the caller counts the evaluation.
 __device__ __forceinline__ void mlp_finish_row(const MlpParams& p, int gr, int leafw, double lr, float V, const float* raw) {
+    if (p.mode == 0 && p.variant == 0 && p.A == 2) {  // CartPole: softmax_seq over two logits, written out (registers only)
+        const float m = raw[1] > raw[0] ? raw[1] : raw[0];
+        const float e0 = det::expf_(__fsub_rn(raw[0], m)), e1 = det::expf_(__fsub_rn(raw[1], m));
+        const float sum = __fadd_rn(__fadd_rn(0.0f, e0), e1);
+        DRow* d = p.drows + (size_t)gr * p.R + (leafw & LEAF_ROW_MASK);
+        d->V = (leafw & LEAF_TERMINAL) ? 0.0f : V;  // mcts.py:406-410
+        *reinterpret_cast<float2*>(d->prior) = make_float2(__fdiv_rn(e0, sum), __fdiv_rn(e1, sum));
+        return;
+    }
     if (p.mode == 0 && p.variant == 1) {
         switch (p.K) {
             case 1: finish_row_continuous<1>(p, gr, leafw, lr, V, raw); return;
