@@ -110,10 +110,16 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
         int mti = p.rng_mt ? (int)mt[MT_N] : 0;
         bool nan = false;
         while (true) {
-            // both children are requested while the scores are computed: the chosen one is then a cache hit instead of a
-            // dependent round trip per level
-            if (row.child[0] != DROW_NONE) asm volatile("prefetch.global.L1 [%0];" ::"l"(rows + row.child[0]));
-            if (row.child[1] != DROW_NONE) asm volatile("prefetch.global.L1 [%0];" ::"l"(rows + row.child[1]));
+            // both children are LOADED while the scores are computed (32 registers): the level costs max(round trip, arithmetic)
+            // instead of their sum, and the next level's children are requested the moment the choice is made
+            const int c0 = row.child[0], c1 = row.child[1];
+            uint4 k0[4], k1[4];
+            {
+                const uint4* s0 = reinterpret_cast<const uint4*>(rows + (c0 != DROW_NONE ? c0 : cur));
+                const uint4* s1 = reinterpret_cast<const uint4*>(rows + (c1 != DROW_NONE ? c1 : cur));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { k0[q] = s0[q]; k1[q] = s1[q]; }
+            }
             // UCT_a = Q_a + prior_a*c_uct*(sqrt(node.n+1)/(n_a+1))   (mcts.py:483-484)
             const double sq = sqrt_small(row.node_n + 1, tb.sq, tb.n);
             double u[2];
@@ -152,10 +158,14 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
             }
             path[levels] = (uint16_t)((cur << 1) | a);
             ++levels;
-            const int child = row.child[a];
+            const int child = a ? c1 : c0;
             if (child == DROW_NONE) break;  // expansion
             cur = child;
-            row = load_drow(rows + cur);
+            {
+                uint4* d = reinterpret_cast<uint4*>(&row);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) d[q] = a ? k1[q] : k0[q];
+            }
             if (row.flags & ROW_TERMINAL) { a = -1; break; }  // trace ends on an existing terminal node
         }
         if (nan) atomicOr(p.err, ERR_NAN);
