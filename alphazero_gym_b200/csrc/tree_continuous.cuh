@@ -276,6 +276,7 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, i
     const int pick = nw > 1 ? u32_to_index(rng_select_u32(p, tree, draws), nw) : 0;
     ++draws;
     if (random_pick) return pick;
+    if (nw == 1) return __ffs((int)win) - 1;  // the usual case without the software find-nth-set routine
     return nw > 0 ? (int)__fns(win, 0, pick + 1) : 0;
 }
 
