@@ -88,3 +88,46 @@ def test_two_rank_selfplay_replay_equals_single_process(tmp_path):
     recs = osp.run(cfg, g["weights"], initial_states(cfg.variant, total, seed=3), steps, 2, seed=cfg.seed, n_threads=1)
     for k in ROW_KEYS:
         assert np.array_equal(got[k], np.concatenate([r[k] for r in recs], 0)), k
+
+
+class _FakeEngine:
+    """Stands in for SearchEngine.set_weights on the CPU (the CUDA engine takes its place on GPUs)."""
+
+    def __init__(self):
+        self.w = None
+
+    def set_weights(self, flat):
+        self.w = flat.detach().clone()
+
+
+def _train_worker(rank, world, port, out_path):
+    """Rank 0 trains (one reference-pinned update on its replay batch), then every rank calls Trainer.push_weights: the flat weights
+    are broadcast from rank 0 (C1) and loaded into each rank's engine, so all ranks search with the trainer's new weights."""
+    from alphazero_gym_b200.network import PolicyNet
+    from alphazero_gym_b200.train import LossConfig, Trainer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_a0c_adam_clip.npz"))
+        torch.set_num_threads(1)
+        net = PolicyNet(3, 128, 3, 6, "elu", num_components=2).load_flat(g["w0"])
+        tr = Trainer(net, LossConfig(tuned=False, tau=0.1, policy_coeff=1, value_coeff=1, alpha=1), optimizer="adam", grad_clip=0.5)
+        if rank == 0:
+            for s in range(3):
+                tr.update(dict(obs=torch.from_numpy(g[f"states_{s}"]), actions=torch.from_numpy(g[f"actions_{s}"]),
+                               counts=torch.from_numpy(g[f"counts_{s}"]), V_target=torch.from_numpy(g[f"V_{s}"])))
+        eng = _FakeEngine()
+        tr.push_weights(eng)
+        np.save(out_path + f".{rank}.npy", eng.w.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_trainer_pushes_rank0_weights_everywhere(tmp_path):
+    out = str(tmp_path / "w")
+    mp.spawn(_train_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    w0, w1 = np.load(out + ".0.npy"), np.load(out + ".1.npy")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_a0c_adam_clip.npz"))
+    assert np.array_equal(w0, w1)                       # rank 1 never trained: it holds rank 0's weights
+    assert np.abs(w0 - g["w_3"]).max() <= 2e-6          # = the reference's weights after the same three updates
+    assert np.abs(w0 - g["w0"]).max() > 1e-4
