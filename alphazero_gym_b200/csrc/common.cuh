@@ -102,6 +102,8 @@ struct TreeParams {
     float gamma_f32, action_bound;
     const uint64_t* seedp;  // Philox key, read from device memory so that azg_set_seed re-keys a captured graph
     int64_t tree_id0;
+    int32_t tree_word;      // launches captured into a CUDA graph: the global id of tree 0 is seedp[1] (and tree_id0 is 0), so that one
+                            // graph serves every tree_id0 (the drop-in classes search with a new id every call)
     // discrete tables
     DRow* drows;      // [B][R]
     double* dstate;   // [B][R][4]
@@ -277,6 +279,9 @@ __device__ __forceinline__ int mt_below_dev(uint32_t* mt, int& mti, int& draws, 
     while ((int)r >= n) r = mt_next_dev(mt, mti, draws) >> (32 - k);
     return (int)r;
 }
+
+// global id of the launch's tree 0 (keys every random stream)
+__device__ __forceinline__ int64_t tree_base(const TreeParams& p) { return p.tree_id0 + (p.tree_word ? (int64_t)__ldg(p.seedp + 1) : 0); }
 
 // stream 0: random.random() / random.choice / random.randint replacements (helpers.py:51, mcts.py:190-192)
 __device__ __forceinline__ uint32_t rng_select_u32(const TreeParams& p, int64_t tree, int draw) {

@@ -109,7 +109,8 @@ struct azg_engine {
     // last search
     int last_B = 0, last_N = 0;
     int64_t launches = 0;
-    std::map<std::tuple<int, int, int, int64_t, int>, cudaGraphExec_t> graphs;
+    std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;  // (B, n_rollouts, tape)
+    int64_t tree_word = 0;  // value of d_seed[1] (global id of tree 0 for graph-captured launches)
 };
 
 static int head_dim_of(const azg_config& c) {
@@ -291,7 +292,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(root_n_init, B);
     ALLOC(err, 1);
     ALLOC(wpack, (size_t)e->wcount);
-    ALLOC(d_seed, 1);
+    ALLOC(d_seed, 2);  // Philox key, global id of tree 0 for graph-captured launches
     ALLOC(stats, 8);
     ALLOC(dtab, 2 * (AZG_TAB + 1));
     if (e->q8) {
@@ -302,6 +303,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
 #undef ALLOC
     CK(cudaMemset(e->err, 0, sizeof(int32_t)));
     CK(cudaMemset(e->stats, 0, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(e->d_seed, 0, 2 * sizeof(uint64_t)));
     CK(cudaMemcpy(e->d_seed, &c.seed, sizeof(uint64_t), cudaMemcpyHostToDevice));
     {
         std::vector<double> tab(2 * (AZG_TAB + 1), 0.0);
@@ -585,8 +587,9 @@ struct Prof {
 };
 
 // enqueue the whole search on `st`; returns the number of kernels launched
-static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStream_t st, cudaError_t* cerr, Prof* prof = nullptr) {
-    const TreeParams p = make_params(e, B, tree_id0);
+static int enqueue_search(azg_engine* e, int B, int N, int64_t tree_id0, cudaStream_t st, cudaError_t* cerr, Prof* prof = nullptr, bool tree_word = false) {
+    TreeParams p = make_params(e, B, tree_word ? 0 : tree_id0);
+    p.tree_word = tree_word ? 1 : 0;
     const MlpParams m = make_mlp_params(e, B);
     const bool tape = p.use_tape != 0;
     int launches = 0;
@@ -669,7 +672,7 @@ static int run_search(azg_engine* e, int B, const double* d_root_state, const in
         if (ce != cudaSuccess) return fail(AZG_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(ce));
     } else {
         const int tape = e->tapeV != nullptr;
-        const auto key = std::make_tuple(B, N, tape, tree_id0, 0);
+        const auto key = std::make_tuple(B, N, tape);  // tree_id0 is read from device memory (TreeParams::tree_word): one graph serves every id
         auto it = e->graphs.find(key);
         if (it == e->graphs.end() || tape) {  // tape pointers may change between calls: always re-capture
             if (it != e->graphs.end()) {
@@ -678,7 +681,7 @@ static int run_search(azg_engine* e, int B, const double* d_root_state, const in
             }
             cudaGraph_t g = nullptr;
             CK(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
-            const int n = enqueue_search(e, B, N, tree_id0, e->own_stream, &ce);
+            const int n = enqueue_search(e, B, N, tree_id0, e->own_stream, &ce, nullptr, true);
             cudaError_t ee = cudaStreamEndCapture(e->own_stream, &g);
             if (ce != cudaSuccess || ee != cudaSuccess) {
                 if (g) cudaGraphDestroy(g);
@@ -697,6 +700,11 @@ static int run_search(azg_engine* e, int B, const double* d_root_state, const in
             it = e->graphs.find(key);
         }
         e->launches = 2 * (int64_t)N + 3 + (e->cfg.variant == AZG_CONTINUOUS ? 1 : 0) - (tape ? N + 1 : 0);
+        if (e->tree_word != tree_id0) {
+            k_set_seed<<<1, 1, 0, st>>>(e->d_seed + 1, (uint64_t)tree_id0);
+            CK(cudaGetLastError());
+            e->tree_word = tree_id0;
+        }
         CK(cudaGraphLaunch(it->second, st));
     }
     e->last_B = B;

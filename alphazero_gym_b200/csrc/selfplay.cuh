@@ -84,14 +84,14 @@ __global__ void k_selfplay_discrete(const SelfPlayParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.B) return;
     const int A = 2;
-    // stable_normalizer (helpers.py:9-27): x = (x / max(x)) ** (1 / temp); pi = |x / sum(x)|
+    // stable_normalizer (helpers.py:9-27): x = (x / max(x)) ** temp; pi = |x / sum(x)|
     double x[2];
     if (p.by_value) { x[0] = p.Q[(size_t)t * p.cmax]; x[1] = p.Q[(size_t)t * p.cmax + 1]; }
     else { x[0] = (double)p.counts[(size_t)t * p.cmax]; x[1] = (double)p.counts[(size_t)t * p.cmax + 1]; }
     const double mx = x[0] > x[1] ? x[0] : x[1];
     for (int i = 0; i < A; ++i) {
         x[i] = x[i] / mx;
-        if (p.temperature != 1.0) x[i] = pow(x[i], 1.0 / p.temperature);  // bit-pinned for temperature == 1 only
+        if (p.temperature != 1.0) x[i] = pow(x[i], p.temperature);  // helpers.py:26; pi itself is bit-pinned for temperature == 1 only
     }
     const double sum = x[0] + x[1];
     const double pi0 = fabs(x[0] / sum), pi1 = fabs(x[1] / sum);

@@ -157,7 +157,7 @@ __device__ __forceinline__ float new_action(const TreeParams& p, int t, int node
     if (p.use_tape) return p.tapeA[(size_t)t * p.R + row];
     {
         const float* hptr = p.chead + ((size_t)t * p.R + node) * p.HS;
-        const int64_t tree = p.tree_id0 + t;
+        const int64_t tree = tree_base(p) + t;
         switch (p.K) {
             case 1: return new_action_k<1>(p, hptr, tree, j);
             case 2: return new_action_k<2>(p, hptr, tree, j);
@@ -176,7 +176,7 @@ __device__ __forceinline__ float new_action(const TreeParams& p, int t, int node
             head[4 * i] = v.x; head[4 * i + 1] = v.y; head[4 * i + 2] = v.z; head[4 * i + 3] = v.w;
         }
     float u, z[AZG_MAX_K];
-    pw_noise(p, p.tree_id0 + t, j, u, z);
+    pw_noise(p, tree_base(p) + t, j, u, z);
     return sample_action(p, head, u, z);
 }
 
@@ -309,7 +309,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
     }
 
     if (SELECT) {
-        const int64_t tree = p.tree_id0 + t;
+        const int64_t tree = tree_base(p) + t;
         int draws = c.draws, n_rows = c.n_rows, pwc = c.pw;
         int cur = 0, sel = -1, kind = KIND_ERROR, depth = 0, nk = c.root_nk;
         uint32_t cur_nn = (uint32_t)c.root_nn;

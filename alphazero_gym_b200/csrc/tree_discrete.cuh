@@ -47,7 +47,7 @@ __device__ __forceinline__ void d_init(const TreeParams& p, int t) {
     p.leaf[t] = 0 | LEAF_EVAL;
     p.n_rows[t] = 1;
     p.draws[t] = 0;
-    if (p.rng_mt) mt_seed_dev(p.mt + (size_t)t * (MT_N + 1), __ldg(p.seedp) + (uint64_t)(p.tree_id0 + t));  // random.seed(seed + tree)
+    if (p.rng_mt) mt_seed_dev(p.mt + (size_t)t * (MT_N + 1), __ldg(p.seedp) + (uint64_t)(tree_base(p) + t));  // random.seed(seed + tree)
     for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
 }
 __global__ void k_init_discrete(const TreeParams p) {
@@ -99,7 +99,7 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
     }
 
     if (SELECT) {
-        const int64_t tree = p.tree_id0 + t;
+        const int64_t tree = tree_base(p) + t;
         int draws = p.draws[t];
         int cur = 0;
         DRow row = load_drow(rows);

@@ -81,6 +81,11 @@ def describe_model(model) -> dict:
     products or PolicyNet): trunk widths, activation, head size, mixture components, log-std clamp."""
     if getattr(model, "layernorm", False):
         raise NotImplementedError("layernorm=True policies are not supported by the CUDA evaluation kernel")
+    cls = type(model).__name__
+    if "Beta" in cls:
+        # GeneralizedBetaPolicy (policies.py:672) has the same parameter shapes as the squashed Normal (head size 2 * action_dim) but
+        # samples from a Beta distribution: evaluating it as a Normal would be silently wrong (and upstream declares it broken)
+        raise NotImplementedError(f"{cls}: only DiscretePolicy, DiagonalNormalPolicy and DiagonalGMMPolicy heads are implemented")
     sd = model.state_dict()
     tw = [k for k in sd if k.startswith("trunk.") and k.endswith(".weight")]
     if not tw or "value_head.weight" not in sd or "dist_head.weight" not in sd:
@@ -99,5 +104,12 @@ def describe_model(model) -> dict:
 
 
 def weights_version(model) -> int:
-    """Cheap change detector: in-place optimizer updates bump every parameter's _version."""
-    return sum(int(p._version) + (p.data_ptr() % 1000003) for p in model.parameters())
+    """Cheap change detector: in-place optimizer updates bump every parameter's _version.  Updates that bypass autograd's version
+    counters -- a training step replayed from a CUDA graph (train.Trainer(cuda_graph=True)) -- must call `bump_weights_version`
+    (Trainer does), or the search classes' `refresh_weights()`."""
+    return sum(int(p._version) + (p.data_ptr() % 1000003) for p in model.parameters()) + int(getattr(model, "_azg_weights_epoch", 0))
+
+
+def bump_weights_version(model) -> None:
+    """Tell every search object that shares `model` that its weights changed (see weights_version)."""
+    model._azg_weights_epoch = int(getattr(model, "_azg_weights_epoch", 0)) + 1

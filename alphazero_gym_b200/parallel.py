@@ -47,5 +47,43 @@ def allgather_results(local: Dict[str, torch.Tensor], total_trees: int) -> Dict[
     return out
 
 
+class PackedRows:
+    """The tensors of one step's replay rows as views into ONE contiguous byte buffer per rank, so that (C2) is a single
+    `all_gather_into_tensor` of that buffer: no per-tensor collectives, no packing copy on the way in, no pad-and-trim.
+
+    Layout per rank (blocks 16-byte aligned): for every key in order, the [B, ...] tensor of that key, row-major.  After the
+    gather the buffer of rank r sits at [r]; `gathered()` returns per-key views of shape [world, B, ...] (global environment
+    order is rank-major because shards are contiguous tree-id ranges of equal size)."""
+
+    def __init__(self, spec, B: int, device):
+        # spec: sequence of (key, trailing shape tuple, dtype)
+        self.B, self.device = int(B), torch.device(device)
+        self.spec, self.off, off = list(spec), {}, 0
+        for key, shape, dtype in self.spec:
+            n = int(np.prod((B,) + tuple(shape))) * torch.empty((), dtype=dtype).element_size()
+            self.off[key] = (off, n)
+            off += (n + 15) // 16 * 16
+        self.nbytes = off
+        self.buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
+        self.views = {key: self.buf[self.off[key][0]:self.off[key][0] + self.off[key][1]].view(dtype).view((B,) + tuple(shape))
+                      for key, shape, dtype in self.spec}
+        self._out = None
+
+    def gathered(self) -> Dict[str, torch.Tensor]:
+        """(C2) one collective for all keys; returns [world * B, ...] tensors in global environment order."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return dict(self.views)
+        world = dist.get_world_size()
+        if self._out is None or self._out.numel() != world * self.nbytes:
+            self._out = torch.empty(world * self.nbytes, dtype=torch.uint8, device=self.device)  # flat: gloo insists on it
+        dist.all_gather_into_tensor(self._out, self.buf)
+        g = self._out.view(world, self.nbytes)
+        out = {}
+        for key, shape, dtype in self.spec:
+            o, n = self.off[key]
+            out[key] = g[:, o:o + n].view(dtype).reshape((world * self.B,) + tuple(shape))
+        return out
+
+
 def results_to_torch(res: Dict[str, np.ndarray], device="cpu") -> Dict[str, torch.Tensor]:
     return {k: torch.from_numpy(np.ascontiguousarray(v)).to(device) for k, v in res.items()}

@@ -104,6 +104,11 @@ class MCTS:
             self._wver[cap] = v
         return eng
 
+    def refresh_weights(self) -> None:
+        """Force the next search to reload `model`'s weights (for updates the version counters cannot see, network.weights_version)."""
+        for cap in self._wver:
+            self._wver[cap] = -1
+
     def close(self) -> None:
         for e in self._engines.values():
             e.close()

@@ -18,7 +18,7 @@ import torch
 from . import _cabi
 from ._cabi import CONTINUOUS, DISCRETE, check
 from .engine import SearchEngine
-from .parallel import allgather_results, broadcast_weights
+from .parallel import PackedRows, allgather_results, broadcast_weights
 
 ROW_KEYS = ("obs", "actions", "counts", "Q", "V_target")  # buffer.store((s, actions, counts, Qs, V)), buffers.py:61
 
@@ -26,13 +26,23 @@ ROW_KEYS = ("obs", "actions", "counts", "Q", "V_target")  # buffer.store((s, act
 def initial_states(variant: int, B: int, seed: int = 34, tree_id0: int = 0, total: Optional[int] = None) -> np.ndarray:
     """Env.reset() for every environment: the same rule as SURVEY 8d configs 3/4 (numpy default_rng(seed) over the GLOBAL
     batch, this shard's slice)."""
-    total = total or (tree_id0 + B)
+    if total is None:
+        # the draw below runs over the GLOBAL batch, so every rank must use the same `total`: tree_id0 + B is only right for a
+        # single shard (or the last one)
+        if _dist_world() > 1:
+            raise ValueError("initial_states: pass total (the global number of environments) when torch.distributed is initialised")
+        total = tree_id0 + B
     rng = np.random.default_rng(seed)
     if variant == DISCRETE:
         s = rng.uniform(-0.05, 0.05, size=(total, 4))
     else:
         s = np.stack([rng.uniform(-np.pi, np.pi, total), rng.uniform(-1.0, 1.0, total)], 1)
     return np.ascontiguousarray(s[tree_id0:tree_id0 + B])
+
+
+def _dist_world() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
 class DeviceReplayBuffer:
@@ -110,7 +120,10 @@ class SelfPlayDriver:
                  temperature: float = 1.0, replay: Optional[DeviceReplayBuffer] = None):
         self.eng, self.B, self.N = engine, int(B), int(n_rollouts)
         self.max_episode_length, self.tree_id0, self.seed = int(max_episode_length), int(tree_id0), int(seed)
-        self.total = int(total_envs or (tree_id0 + B))
+        if total_envs is None:
+            # equal shards of B environments per rank (bench.py, the gloo tests); a ragged split must say its total
+            total_envs = _dist_world() * B if _dist_world() > 1 else tree_id0 + B
+        self.total = int(total_envs)
         self.deterministic = bool(deterministic)
         self.by_value = final_selection == "max_value"  # any other value means visit counts (agents.py:294-301)
         self.temperature = float(temperature)
@@ -122,17 +135,19 @@ class SelfPlayDriver:
         self.variant = cfg.variant
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
         self.env_state = torch.from_numpy(initial_states(cfg.variant, B, seed, tree_id0, self.total)).to(dev)
-        self.t = dict(ep_step=z(B, torch.int32), episode=z(B, torch.int32), root_n=z(B, torch.int32),
-                      obs=z((B, S), torch.float32), actions=z((B, cm), torch.float32), counts=z((B, cm), torch.int32),
-                      Q=z((B, cm), torch.float64), V_target=z(B, torch.float64), n_children=z(B, torch.int32),
-                      action_taken=z(B, torch.float32), reward=z(B, torch.float64), done=z(B, torch.int32))
+        # the replay row of a step (ROW_KEYS) lives in ONE byte buffer, so that its all-gather is a single collective (parallel.PackedRows)
+        self.packed = PackedRows([("Q", (cm,), torch.float64), ("V_target", (), torch.float64), ("obs", (S,), torch.float32),
+                                  ("actions", (cm,), torch.float32), ("counts", (cm,), torch.int32)], B, dev)
+        self.t = dict(ep_step=z(B, torch.int32), episode=z(B, torch.int32), root_n=z(B, torch.int32), n_children=z(B, torch.int32),
+                      action_taken=z(B, torch.float32), reward=z(B, torch.float64), done=z(B, torch.int32), **self.packed.views)
         t = self.t
         self._io = _cabi.SelfPlayIO(self.env_state.data_ptr(), t["ep_step"].data_ptr(), t["episode"].data_ptr(),
                                     t["root_n"].data_ptr() if cfg.variant == DISCRETE else None, t["obs"].data_ptr(),
                                     t["actions"].data_ptr(), t["counts"].data_ptr(), t["Q"].data_ptr(), t["V_target"].data_ptr(),
                                     t["n_children"].data_ptr(), t["action_taken"].data_ptr(), t["reward"].data_ptr(),
                                     t["done"].data_ptr())
-        self.episode_return = z(B, torch.float64)
+        self.episode_return = z(B, torch.float64)  # return of the running episode (of the finished one where done is set)
+        self._prev_done = torch.zeros(B, dtype=torch.bool, device=dev)
 
     def set_states(self, states: np.ndarray) -> None:
         self.env_state.copy_(torch.from_numpy(np.ascontiguousarray(states, np.float64)).to(self.env_state.device))
@@ -146,7 +161,8 @@ class SelfPlayDriver:
                                              self.temperature, torch.cuda.current_stream().cuda_stream))
         eng.last_B = self.B
         self.step_index += 1
-        self.episode_return += self.t["reward"]
+        self.episode_return = torch.where(self._prev_done, torch.zeros_like(self.episode_return), self.episode_return) + self.t["reward"]
+        self._prev_done = self.t["done"] != 0  # the NEXT step starts a new episode for these environments
         if store and self.replay is not None:
             self.replay.store(self.rows())
         return self.t
@@ -155,7 +171,10 @@ class SelfPlayDriver:
         return {k: self.t[k] for k in ROW_KEYS}
 
     def gathered_rows(self) -> Dict[str, torch.Tensor]:
-        """(C2) this step's replay rows of every rank, in global environment order."""
+        """(C2) this step's replay rows of every rank, in global environment order: ONE all_gather_into_tensor of the packed row
+        buffer when every rank owns B environments (the sharding of bench.py), the per-tensor pad-and-trim gather otherwise."""
+        if self.total == _dist_world() * self.B:
+            return self.packed.gathered()
         return allgather_results(self.rows(), self.total)
 
     def sync_weights(self, flat: torch.Tensor, src: int = 0) -> None:

@@ -27,7 +27,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .network import PolicyNet
+from .network import PolicyNet, bump_weights_version
 
 _LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
 
@@ -154,7 +154,15 @@ def make_optimizer(name: str, params, lr: float = 0.001, capturable: bool = Fals
 def root_children(c_pw: float, kappa: float, n_rollouts: int) -> int:
     """Children of the root after a finished continuous search: the progressive-widening limit at the last root visit count
     (states.py:252-275 with n = n_rollouts - 1)."""
-    return int(math.ceil(c_pw * float(n_rollouts) ** kappa))
+    # The root holds one action before the first simulation (mcts.py:673) and gains AT MOST one per simulation, when
+    # ceil(c_pw * (n + 1)^kappa) exceeds its child count at root visit count n (mcts.py:725-727): with a large c_pw and few
+    # rollouts the closed form ceil(c_pw * N^kappa) over-counts (c_pw = 3, N = 2: 3 children, not 5), and the padded columns
+    # (count 0) would put log(0) into the loss.
+    kids = 1
+    for n in range(n_rollouts):
+        if int(math.ceil(c_pw * float(n + 1) ** kappa)) > kids:
+            kids += 1
+    return kids
 
 
 class Trainer:
@@ -195,6 +203,7 @@ class Trainer:
         for k, t in static_in.items():
             t.copy_(batch[k], non_blocking=True)
         graph.replay()
+        bump_weights_version(self.net)  # graph replays do not touch Parameter._version: drop-in search objects sharing the net must reload
         return {k: v.clone() for k, v in static_out.items()}
 
     def _capture(self, batch):

@@ -54,6 +54,14 @@ CASES = {
     "pendulum_n40_cpw2_onpolicy": dict(cfg=azo.continuous_config(n_rollouts=40, c_pw=2.0, kappa=0.4,
                                                                  V_target_policy="on_policy"), B=8),
     "pendulum_n30_k3": dict(cfg=azo.continuous_config(n_rollouts=30, num_components=3), B=6),
+    # V_target_policy "greedy" (mcts.py:133-173; from a non-terminal root its loop never runs, so it is the root's Q.max())
+    "cartpole_n8_greedy": dict(cfg=azo.discrete_config(n_rollouts=8, epsilon=0.1, V_target_policy="greedy"), B=8),
+    "pendulum_n25_greedy": dict(cfg=azo.continuous_config(n_rollouts=25, V_target_policy="greedy"), B=6),
+    # TRAINED weights: the reference agent after 80 real `update` steps (agents.py:319-389, :539-603; lr 3e-3 so that the activation
+    # range moves well away from the default initialisation), then its search -- the case the per-row block exponent of the
+    # tensor-core evaluation has to survive
+    "cartpole_n50_trained": dict(cfg=azo.discrete_config(n_rollouts=50, epsilon=0.1), B=8, trained=80),
+    "pendulum_n50_trained": dict(cfg=azo.continuous_config(n_rollouts=50), B=8, trained=80),
 }
 
 
@@ -82,11 +90,34 @@ def roots_for(case) -> np.ndarray:
     return pendulum_roots(B)
 
 
+def trained_model(cfg: azo.Config, updates: int):
+    """The reference's own agent (hydra / omegaconf stubbed at import time only, oracle/gen_train_golden.py) after `updates`
+    gradient steps of its unmodified `update` on seeded synthetic replay batches; returns its policy network."""
+    from . import gen_train_golden as GT
+    import torch
+    GT.install_stubs()
+    from alphazero.agent import agents  # type: ignore
+    torch.manual_seed(34)
+    torch.set_num_threads(1)
+    cont = cfg.variant == azo.CONTINUOUS
+    loss = dict(_target_="alphazero.agent.losses.A0CLoss", tau=0.1, policy_coeff=1, alpha=1, value_coeff=1, reduction="mean")
+    opt = dict(GT.RMSPROP, lr=0.003)
+    if cont:
+        agent = agents.ContinuousAgent(policy_cfg=GT.CONT_POLICY, mcts_cfg=GT.MCTS_C, loss_cfg=loss, optimizer_cfg=opt,
+                                       final_selection="max_visit", epsilon=0, train_epochs=1, grad_clip=0.0, device="cpu")
+    else:
+        agent = agents.DiscreteAgent(policy_cfg=GT.DISC_POLICY, mcts_cfg=GT.MCTS_D, loss_cfg=loss, optimizer_cfg=opt,
+                                     final_selection="max_visits", train_epochs=1, grad_clip=0.0, temperature=1.0, device="cpu")
+    for s in range(updates):
+        agent.update(tuple(a.copy() for a in GT.make_batch(cont, s)))
+    return agent.nn
+
+
 def generate(name: str) -> str:
     case = CASES_ALL[name]
     cfg: azo.Config = case["cfg"]
     cfg.math_mode = azo.MATH_LIBM
-    model = RH.make_model(cfg, weight_seed=34)
+    model = trained_model(cfg, case["trained"]) if case.get("trained") else RH.make_model(cfg, weight_seed=34)
     roots = roots_for(case)
     if cfg.variant == azo.DISCRETE:
         out = RH.run_discrete(cfg, model, roots, second_search=case.get("second_search", False))

@@ -31,7 +31,7 @@ def _unit(x: int) -> float:
 
 
 def stable_normalizer(x: np.ndarray, temp: float) -> np.ndarray:
-    x = (x / np.max(x)) ** (1 / temp)
+    x = (x / np.max(x)) ** temp  # helpers.py:26
     return np.abs(x / np.sum(x))
 
 

@@ -38,16 +38,23 @@ def _mask_root_r(x, key):
     return x
 
 
-def assert_tree_equal(got, ref, discrete, exact_fp=True, skip=()):
+def assert_tree_equal(got, ref, discrete, exact_fp=True, skip=(), results_only=False):
     """exact_fp=True: every array bit-identical.  False: ints bit-identical, FP within tolerance."""
     ints = (DISCRETE_INT if discrete else CONT_INT) + RES_INT
     fps = (DISCRETE_FP if discrete else CONT_FP) + RES_FP
+    # a comparison that silently loses a field passes for the wrong reason: every key of the table layout must be on both sides
+    # (callers that compare root results only pass dump-less dicts on BOTH sides and say so with results_only=True)
+    want = (RES_INT + RES_FP) if results_only else ints + fps
+    missing = [k for k in want if k not in skip and (k not in got or k not in ref)]
+    assert not missing, f"arrays missing from the comparison: {missing}"
+    if results_only:
+        ints, fps = RES_INT, RES_FP
     for k in ints:
-        if k in skip or k not in ref or k not in got:
+        if k in skip:
             continue
         assert np.array_equal(got[k], ref[k]), f"integer array {k} differs at {np.argwhere(got[k] != ref[k])[:4].tolist()}"
     for k in fps:
-        if k in skip or k not in ref or k not in got:
+        if k in skip:
             continue
         a, b = _mask_root_r(got[k], k), _mask_root_r(ref[k], k)
         if exact_fp:

@@ -91,3 +91,27 @@ def test_selfplay_is_shard_invariant():
     for f, h in zip(full, half):
         for k in KEYS + CARRY:
             assert np.array_equal(f[k][16:], h[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["selfplay_cartpole_t1", "selfplay_cartpole_t05", "selfplay_cartpole_t2", "selfplay_cartpole_value_t2",
+                                  "selfplay_cartpole_det", "selfplay_pendulum_k2", "selfplay_pendulum_value"])
+@pytest.mark.parametrize("q8", [False, True])
+def test_selfplay_engine_vs_reference_agents(name, q8):
+    """azg_selfplay_step against (1) the oracle loop, bit for bit, and (2) the goldens of the UNMODIFIED reference agents
+    (DiscreteAgent.act / ContinuousAgent.act + mcts_forward / reset_mcts, oracle/gen_selfplay_golden.py): integers and the chosen
+    discrete actions bit-exact, floating point within 1e-5.  Temperature 0.5 / 2, max_value and deterministic selection included --
+    the cases that tell x ** temp (helpers.py:26) from x ** (1 / temp)."""
+    from oracle import gen_selfplay_golden as GS
+    import test_selfplay_golden as TG
+    cfg, meta, g = GS.load(name)
+    cfg.math_mode, cfg.use_eval_tape = azo.MATH_DET, 0
+    if q8:
+        cfg.eval_mode = azo.EVAL_Q8
+    kw = dict(deterministic=meta["deterministic"], temperature=meta["temperature"])
+    ref = osp.run(cfg, g["weights"], g["states0"], meta["steps"], meta["max_episode_length"], seed=cfg.seed, tree_id0=meta["tree_id0"],
+                  by_value=meta["final_selection"] == "max_value", **kw)
+    got, _, _ = _run_engine(cfg, g["weights"], g["states0"], meta["steps"], meta["max_episode_length"], tree_id0=meta["tree_id0"],
+                            final_selection=meta["final_selection"], **kw)
+    _compare(got, ref, cfg.cmax)
+    TG.compare_with_golden(got, g, cfg.variant == azo.DISCRETE)

@@ -131,3 +131,39 @@ def test_two_rank_trainer_pushes_rank0_weights_everywhere(tmp_path):
     assert np.array_equal(w0, w1)                       # rank 1 never trained: it holds rank 0's weights
     assert np.abs(w0 - g["w_3"]).max() <= 2e-6          # = the reference's weights after the same three updates
     assert np.abs(w0 - g["w0"]).max() > 1e-4
+
+
+def _packed_worker(rank, world, port, B, out_path):
+    """(C2) as ONE collective: the step's replay rows live in one byte buffer per rank (parallel.PackedRows) and a single
+    all_gather_into_tensor moves them; the gathered views must equal the per-tensor gather in global environment order."""
+    from alphazero_gym_b200.parallel import PackedRows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cm, S = 5, 3
+        pk = PackedRows([("Q", (cm,), torch.float64), ("V_target", (), torch.float64), ("obs", (S,), torch.float32),
+                         ("actions", (cm,), torch.float32), ("counts", (cm,), torch.int32)], B, "cpu")
+        rng = np.random.default_rng(100 + rank)
+        pk.views["Q"].copy_(torch.from_numpy(rng.standard_normal((B, cm))))
+        pk.views["V_target"].copy_(torch.from_numpy(rng.standard_normal(B)))
+        pk.views["obs"].copy_(torch.from_numpy(rng.standard_normal((B, S)).astype(np.float32)))
+        pk.views["actions"].copy_(torch.from_numpy(rng.standard_normal((B, cm)).astype(np.float32)))
+        pk.views["counts"].copy_(torch.from_numpy(rng.integers(0, 25, (B, cm)).astype(np.int32)))
+        one = pk.gathered()
+        five = allgather_results({k: v.clone() for k, v in pk.views.items()}, world * B)
+        for k in one:
+            assert one[k].shape == five[k].shape and torch.equal(one[k], five[k]), k
+        if rank == 0:
+            np.savez(out_path, **{k: v.numpy() for k, v in one.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_rows_single_collective_equals_per_tensor_gather(tmp_path):
+    out = str(tmp_path / "packed.npz")
+    B = 7  # odd: the blocks of the byte buffer need their 16-byte padding
+    mp.spawn(_packed_worker, args=(2, _free_port(), B, out), nprocs=2, join=True)
+    got = np.load(out)
+    rng0, rng1 = np.random.default_rng(100), np.random.default_rng(101)
+    assert np.array_equal(got["Q"], np.concatenate([rng0.standard_normal((B, 5)), rng1.standard_normal((B, 5))]))
+    assert got["counts"].shape == (2 * B, 5) and got["obs"].dtype == np.float32
