@@ -24,6 +24,7 @@
 #include "mlp.cuh"
 #include "qmlp.cuh"
 #include "qmlp2.cuh"
+#include "search_wg.cuh"
 #include "selfplay.cuh"
 #include "tree_continuous.cuh"
 #include "tree_discrete.cuh"
@@ -71,6 +72,9 @@ struct azg_engine {
     double* dtab = nullptr;      // rcp_tab[AZG_TAB + 1], sqrt_tab[AZG_TAB + 1] (common.cuh div_small)
     // AZG_FLAG_EVAL_Q8: int8 digit planes + f32 side table of the tensor-core evaluation kernel (qmlp.cuh)
     int8_t* qdigits = nullptr;
+    int8_t* qdigits_nat = nullptr;  // rows in natural order (search_wg.cuh)
+    bool fused_v1 = false;          // AZG_FUSED_V1=1: the two-phase whole-search kernel of qmlp2.cuh instead of search_wg.cuh
+    size_t wg_smem = 0;
     float* qfl = nullptr;
     int qfl_count = 0;
     size_t qmlp_smem = 0;
@@ -135,7 +139,7 @@ extern "C" void azg_destroy(azg_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     void* ptrs[] = {e->drows, e->dstate, e->crows, e->hot_block, e->chead, e->pw_table, e->n_rows, e->draws,
-                    e->leaf, e->path, e->dpath, e->ddepth, e->mt, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qfl, e->r_actions,
+                    e->leaf, e->path, e->dpath, e->ddepth, e->mt, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qdigits_nat, e->qfl, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -200,6 +204,8 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     if (e->q8) {
         e->qfl_count = (c.state_dim * H + H + (c.n_hidden - 1) * 2 * H + H * e->PO_PAD + e->PO_PAD + 3) / 4 * 4;
         e->qmlp_smem = qmlp2_smem_bytes(c.n_hidden - 1, e->qfl_count, (c.flags & AZG_FLAG_FUSED) != 0);
+        e->wg_smem = search_wg_smem_bytes(c.n_hidden - 1, e->qfl_count);
+        e->fused_v1 = getenv("AZG_FUSED_V1") != nullptr;
         if (H != 128 || c.n_hidden < 2 || c.n_hidden > 3 || e->PO_PAD > Q2_MAX_PO || e->qmlp_smem > (size_t)prop.sharedMemPerBlockOptin ||
             prop.major != 10) {
             delete e;
@@ -297,6 +303,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(dtab, 2 * (AZG_TAB + 1));
     if (e->q8) {
         ALLOC(qdigits, (size_t)(c.n_hidden - 1) * 3 * QMLP_PLANE);
+        ALLOC(qdigits_nat, (size_t)(c.n_hidden - 1) * 3 * QMLP_PLANE);
         ALLOC(qfl, (size_t)e->qfl_count);
     }
     ALLOC(r_actions, B * e->cmax); ALLOC(r_counts, B * e->cmax); ALLOC(r_Q, B * e->cmax); ALLOC(r_Vt, B); ALLOC(r_nchild, B);
@@ -368,7 +375,7 @@ static void pack_weights(const azg_engine* e, const float* w, std::vector<float>
 // AZG_FLAG_EVAL_Q8 packing (contract: oracle/azg_oracle.h "AZO_EVAL_Q8"; consumer: qmlp.cuh).  Hidden layer l >= 1, output j:
 // e = clamp(biased_exponent(max_k |W[j][k]| * 1.004f), 32, 200); Wq = rni(W * 2^(149-e)); balanced base-256 digits = bytes of
 // (Wq + 0x8080) ^ 0x8080; planes (hi, mid, lo) in the UMMA K-major canonical layout [k/16][j][16]; cw[j] = 2^(e-133).
-static void pack_weights_q8(const azg_engine* e, const float* w, std::vector<int8_t>& digits, std::vector<float>& fl) {
+static void pack_weights_q8(const azg_engine* e, const float* w, std::vector<int8_t>& digits, std::vector<float>& fl, bool natural_rows = false) {
     const int H = e->cfg.hidden, S = e->cfg.state_dim, L = e->cfg.n_hidden, P = e->P, PO = e->PO_PAD;
     digits.assign((size_t)(L - 1) * 3 * QMLP_PLANE, 0);
     fl.assign(e->qfl_count, 0.0f);
@@ -398,6 +405,13 @@ static void pack_weights_q8(const azg_engine* e, const float* w, std::vector<int
                 const float tv = tq;
                 int32_t q = tv != tv ? 0 : (tv >= 2147483648.0f ? INT32_MAX : (tv <= -2147483648.0f ? INT32_MIN : (int32_t)nearbyintf(tv)));
                 const uint32_t t = ((uint32_t)q + 0x8080u) ^ 0x8080u;
+                if (natural_rows) {  // search_wg.cuh: [k/16][step of 16 outputs][plane][16 rows][16 B]
+                    const size_t o = (size_t)(k / 16) * WG_B_KCHUNK + (size_t)(j / 16) * WG_B_STEP + (size_t)(j % 16) * 16 + (k % 16);
+                    pl[o] = (int8_t)((t >> 16) & 0xFF);
+                    pl[o + 256] = (int8_t)((t >> 8) & 0xFF);
+                    pl[o + 512] = (int8_t)(t & 0xFF);
+                    continue;
+                }
                 const size_t o = (size_t)(k / 16) * 2048 + (size_t)qmlp_perm_row(j) * 16 + (k % 16);
                 pl[o] = (int8_t)((t >> 16) & 0xFF);
                 pl[QMLP_PLANE + o] = (int8_t)((t >> 8) & 0xFF);
@@ -443,6 +457,11 @@ extern "C" int azg_set_weights(azg_engine* e, const float* flat, int64_t n, void
     if (e->q8) {
         pack_weights_q8(e, host.data(), qd, qf);
         CK(cudaMemcpyAsync(e->qdigits, qd.data(), qd.size(), cudaMemcpyHostToDevice, st));
+        std::vector<int8_t> qn;
+        std::vector<float> qf2;
+        pack_weights_q8(e, host.data(), qn, qf2, true);
+        CK(cudaMemcpyAsync(e->qdigits_nat, qn.data(), qn.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // qn is a local
         CK(cudaMemcpyAsync(e->qfl, qf.data(), qf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     CK(cudaStreamSynchronize(st));
@@ -492,7 +511,7 @@ static MlpParams make_mlp_params(const azg_engine* e, int n) {
     m.leaf = e->leaf; m.drows = e->drows; m.crows = e->crows; m.chead = e->chead; m.evals = e->ctr + (size_t)3 * n;
     m.ctl = e->ctl; m.et = e->et; m.BS = c.max_trees; m.gamma_f32 = (float)c.gamma;
     m.head_dim = azg_head_dim(e);
-    m.qdigits = e->qdigits; m.qfl = e->qfl; m.qfl_count = e->qfl_count;
+    m.qdigits = e->qdigits; m.qdigits_nat = e->qdigits_nat; m.qfl = e->qfl; m.qfl_count = e->qfl_count;
     m.stats = e->stats;
     return m;
 }
@@ -524,7 +543,15 @@ static cudaError_t launch_qmlp_t(const azg_engine* e, const MlpParams& m, cudaSt
     if (set_attr) {
         cudaError_t ce = cudaFuncSetAttribute(k_qmlp2<S, ACT, NL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
         if (ce != cudaSuccess) return ce;
-        return cudaFuncSetAttribute(k_qmlp2<S, ACT, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
+        ce = cudaFuncSetAttribute(k_qmlp2<S, ACT, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
+        if (ce != cudaSuccess) return ce;
+        // search_wg.cuh raises its 16 tree + evaluation warps to 104 registers with setmaxnreg: the CTA's pool (640 threads x the
+        // kernel's register count) must hold 512 x 104 + 128 x 56, or the instruction would wait forever
+        cudaFuncAttributes fa;
+        ce = cudaFuncGetAttributes(&fa, k_search_wg<S, ACT, NL>);
+        if (ce != cudaSuccess) return ce;
+        if (fa.numRegs * WG_THREADS < WG_EPI_THREADS * 104 + 128 * 56) return cudaErrorLaunchOutOfResources;
+        return cudaFuncSetAttribute(k_search_wg<S, ACT, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->wg_smem);
     }
     const int grid = std::max(1, std::min((m.n + 127) / 128, e->sm_count));
     TreeParams none;
@@ -538,8 +565,16 @@ static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const
     const int chunk = e->sm_count * Q2_MAX_TILES * 128;
     for (int lo = 0; lo < p.B; lo += chunk) {
         const int hi = std::min(p.B, lo + chunk);
-        const int grid = std::max(1, std::min((hi - lo + 127) / 128, e->sm_count));
-        cudaError_t ce = launch_ex(e, k_qmlp2<S, ACT, NL, true>, grid, Q2_THREADS, e->qmlp_smem, st, m, p, N, lo, hi);
+        cudaError_t ce;
+        if (e->fused_v1) {
+            const int grid = std::max(1, std::min((hi - lo + 127) / 128, e->sm_count));
+            ce = launch_ex(e, k_qmlp2<S, ACT, NL, true>, grid, Q2_THREADS, e->qmlp_smem, st, m, p, N, lo, hi);
+        } else {
+            // four warpgroups per CTA, each with its own tile: small batches are spread over every SM (a CTA's trees over its four
+            // warpgroups), large ones use all SMs with up to WG_MAX_ROUNDS x 4 tiles each
+            const int grid = std::max(1, std::min((hi - lo + 3) / 4, e->sm_count));
+            ce = launch_ex(e, k_search_wg<S, ACT, NL>, grid, WG_THREADS, e->wg_smem, st, m, p, N, lo, hi);
+        }
         ++*launches;
         if (ce != cudaSuccess) return ce;
     }

@@ -49,6 +49,7 @@ struct MlpParams {
     int32_t head_dim;
     // AZG_FLAG_EVAL_Q8 (qmlp.cuh): int8 digit planes [L-1][3][H/16][H][16] and the f32 side table (engine.cu pack_weights_q8)
     const int8_t* qdigits;
+    const int8_t* qdigits_nat;  // the same digit planes with the rows in natural order (search_wg.cuh)
     const float* qfl;
     int32_t qfl_count;  // floats in qfl (multiple of 4)
     // whole-search kernel: cycle accounting, summed over CTAs (azg_fused_stats, include/azg.h)
@@ -105,8 +106,7 @@ template <int ACT>
 __device__ __forceinline__ float mlp_act(float v) {
     if (ACT == 0) return v > 0.0f ? v : 0.0f;  // ReLU (DiscretePolicy.yaml:8)
     // ELU alpha=1 (ContinuousPolicy.yaml:9): v > 0 ? v : expm1(v), expm1 = det::expm1f_ written with selects.
-    // (n == 0 needs no special case: fma(p, 1, 0) == p; x < -17.5 is selected to -1 like the reference form; for v > 0 the
-    // exponential branch is computed on garbage and discarded.)
+    // (n == 0 needs no special case: fma(p, 1, 0) == p; for v > 0 the exponential branch is computed on garbage and discarded.)
     const float xx = fmaxf(v, -20.0f);
     const float tm = __fadd_rn(__fmul_rn(xx, 1.44269504088896341f), MLP_RINT_MAGIC);
     const float n = __fsub_rn(tm, MLP_RINT_MAGIC);
@@ -115,9 +115,11 @@ __device__ __forceinline__ float mlp_act(float v) {
     const float pl = det::expm1_poly(r);
     const float t = mlp_pow2_of_magic(tm);
     const float e = __fmaf_rn(pl, t, __fsub_rn(t, 1.0f));
-    float res = v < -17.5f ? -1.0f : e;
-    res = v > 0.0f ? v : res;
-    return (v != v) ? v : res;
+    // Two selects of the reference form are redundant here and dropped (same bits, two FSETP + two FSEL fewer per element on the
+    // evaluation kernels' critical pipe): for EVERY f32 v < -17.5 the clamped evaluation already yields exactly -1.0f (t <= 2^-25,
+    // so t - 1 and the final fma round to -1; checked exhaustively over all 1 039 400 960 such values, tools/elu_check.c), and
+    // "v <= 0 ? e : v" passes a NaN through by itself.
+    return v <= 0.0f ? e : v;
 }
 
 // the same activation on a pair, with the FMA-pipe work packed into f32x2 instructions (each half is the scalar
@@ -141,14 +143,7 @@ __device__ __forceinline__ float2 mlp_act2(float2 v) {
     const float2 pl = __ffma2_rn(p, z, r);
     const float2 t = make_float2(mlp_pow2_of_magic(tm.x), mlp_pow2_of_magic(tm.y));
     const float2 e = __ffma2_rn(pl, t, __fadd2_rn(t, make_float2(-1.0f, -1.0f)));
-    float2 res;
-    res.x = v.x < -17.5f ? -1.0f : e.x;
-    res.y = v.y < -17.5f ? -1.0f : e.y;
-    res.x = v.x > 0.0f ? v.x : res.x;
-    res.y = v.y > 0.0f ? v.y : res.y;
-    res.x = (v.x != v.x) ? v.x : res.x;
-    res.y = (v.y != v.y) ? v.y : res.y;
-    return res;
+    return make_float2(v.x <= 0.0f ? e.x : v.x, v.y <= 0.0f ? e.y : v.y);  // see mlp_act: the saturation and NaN selects are redundant
 }
 
 // post-processing of one row's raw head outputs (policies.py:275-297 softmax priors; :617-631 GMM params)

@@ -23,7 +23,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     int spins = 0;
     while (!mbar_try_wait_hint(bar, parity, 20000u)) {
-        if (++spins > (1 << 22)) __trap();  // seconds
+        if (++spins > (1 << 22)) {  // seconds
+            printf("mbar_wait timeout: block %d thread %d barrier smem 0x%x parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
     }
 }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {  // no swizzle, K-major, LBO 2048 B, SBO 128 B, descriptor version 1

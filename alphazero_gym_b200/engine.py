@@ -259,7 +259,7 @@ class SearchEngine:
         check(self._lib.azg_fused_stats(self._h, C.byref(arr)))
         tot = max(1, int(arr[0]))
         return {"ctas": int(arr[4]), "kernel_cycles_per_cta": tot / max(1, int(arr[4])), "tree_phase": arr[1] / tot,
-                "wait_for_post_processing": arr[2] / tot}
+                "wait_for_post_processing": arr[2] / tot, "x_wait_mma": arr[3] / tot}
 
     # ---- standalone kernels (known-answer tests) ---------------------------------------------------------
     def mlp_forward(self, x: np.ndarray):
