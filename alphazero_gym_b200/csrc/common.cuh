@@ -134,11 +134,20 @@ struct TreeParams {
     const double* root_state;
     const int32_t* root_n_init;
     int32_t* err;
+    unsigned long long* prof;  // AZG_TREE_PROF builds: cycle accounting of the tree step per section (warp time, lane 0)
     // evaluator injection (parity level A)
     const float* tapeV;
     const float* tapeP;
     const float* tapeA;
 };
+
+#ifdef AZG_TREE_PROF
+#define TP_BEGIN() long long tp_last = clock64()
+#define TP_STAMP(k) do { const long long _t = clock64(); if ((threadIdx.x & 31) == 0 && p.prof) atomicAdd(p.prof + (k), (unsigned long long)(_t - tp_last)); tp_last = _t; } while (0)
+#else
+#define TP_BEGIN()
+#define TP_STAMP(k)
+#endif
 
 // ---- IEEE division by a small integer without the division routine ------------------------------------------------
 // Q = W / n and sqrt(N + 1) / (n + 1) sit on the select chain between two dependent loads, and DDIV / DSQRT are ~40-instruction

@@ -73,7 +73,7 @@ struct azg_engine {
     // AZG_FLAG_EVAL_Q8: int8 digit planes + f32 side table of the tensor-core evaluation kernel (qmlp.cuh)
     int8_t* qdigits = nullptr;
     int8_t* qdigits_nat = nullptr;  // rows in natural order (search_wg.cuh)
-    bool fused_v1 = false;          // AZG_FUSED_V1=1: the two-phase whole-search kernel of qmlp2.cuh instead of search_wg.cuh
+    int fused_mode = 0;             // 0: whole-search kernel chosen by batch size; 1: two-phase (qmlp2.cuh); 2: warpgroups (search_wg.cuh)
     size_t wg_smem = 0;
     float* qfl = nullptr;
     int qfl_count = 0;
@@ -205,7 +205,10 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
         e->qfl_count = (c.state_dim * H + H + (c.n_hidden - 1) * 2 * H + H * e->PO_PAD + e->PO_PAD + 3) / 4 * 4;
         e->qmlp_smem = qmlp2_smem_bytes(c.n_hidden - 1, e->qfl_count, (c.flags & AZG_FLAG_FUSED) != 0);
         e->wg_smem = search_wg_smem_bytes(c.n_hidden - 1, e->qfl_count);
-        e->fused_v1 = getenv("AZG_FUSED_V1") != nullptr;
+        // AZG_FUSED_KERNEL=two_phase | warpgroups forces one whole-search kernel (experiments); default: by batch size (launch_fused_t)
+        const char* fk = getenv("AZG_FUSED_KERNEL");
+        e->fused_mode = !fk ? 0 : (fk[0] == 't' ? 1 : 2);
+        if (getenv("AZG_FUSED_V1")) e->fused_mode = 1;
         if (H != 128 || c.n_hidden < 2 || c.n_hidden > 3 || e->PO_PAD > Q2_MAX_PO || e->qmlp_smem > (size_t)prop.sharedMemPerBlockOptin ||
             prop.major != 10) {
             delete e;
@@ -299,7 +302,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(err, 1);
     ALLOC(wpack, (size_t)e->wcount);
     ALLOC(d_seed, 2);  // Philox key, global id of tree 0 for graph-captured launches
-    ALLOC(stats, 8);
+    ALLOC(stats, 16);
     ALLOC(dtab, 2 * (AZG_TAB + 1));
     if (e->q8) {
         ALLOC(qdigits, (size_t)(c.n_hidden - 1) * 3 * QMLP_PLANE);
@@ -309,7 +312,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     ALLOC(r_actions, B * e->cmax); ALLOC(r_counts, B * e->cmax); ALLOC(r_Q, B * e->cmax); ALLOC(r_Vt, B); ALLOC(r_nchild, B);
 #undef ALLOC
     CK(cudaMemset(e->err, 0, sizeof(int32_t)));
-    CK(cudaMemset(e->stats, 0, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(e->stats, 0, 16 * sizeof(unsigned long long)));
     CK(cudaMemset(e->d_seed, 0, 2 * sizeof(uint64_t)));
     CK(cudaMemcpy(e->d_seed, &c.seed, sizeof(uint64_t), cudaMemcpyHostToDevice));
     {
@@ -497,6 +500,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path; p.dpath = e->dpath; p.ddepth = e->ddepth; p.mt = e->mt; p.rng_mt = e->mt != nullptr;
     p.ctr = e->ctr; p.X = e->X; p.root_state = e->root_state; p.root_n_init = e->root_n_init; p.err = e->err;
     p.tapeV = e->tapeV; p.tapeP = e->tapeP; p.tapeA = e->tapeA;
+    p.prof = e->stats + 8;
     return p;
 }
 
@@ -566,7 +570,14 @@ static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const
     for (int lo = 0; lo < p.B; lo += chunk) {
         const int hi = std::min(p.B, lo + chunk);
         cudaError_t ce;
-        if (e->fused_v1) {
+        // Which whole-search kernel: measured on B200 (profiles/README.md r2c, trees per GPU -> M sims/s, Pendulum N = 100):
+        //   two-phase (qmlp2.cuh)     8192: 332   16384: 641   32768: 934   65536: 1056   131072:  962
+        //   warpgroups (search_wg)    8192: 155   16384: 292   32768: 571   65536: 1113   131072: 1050
+        // A warpgroup evaluates its tile alone (one thread per row, all 128 columns), so a simulation never takes less than ~52 us;
+        // in the two-phase kernel 16 warps share a tile and a thin batch finishes a simulation in ~24 us.  From about three full
+        // tiles per SM on, the independent warpgroups win (the tree step of one hides under the evaluation of the others).
+        const bool two_phase = e->fused_mode == 1 || (e->fused_mode == 0 && (hi - lo) < 3 * 128 * e->sm_count);
+        if (two_phase) {
             const int grid = std::max(1, std::min((hi - lo + 127) / 128, e->sm_count));
             ce = launch_ex(e, k_qmlp2<S, ACT, NL, true>, grid, Q2_THREADS, e->qmlp_smem, st, m, p, N, lo, hi);
         } else {
@@ -1020,9 +1031,13 @@ extern "C" int azg_fused_stats(azg_engine* e, int64_t out[8]) {
     if (!e || !out) return fail(AZG_EINVAL, "null argument");
     CK(cudaSetDevice(e->cfg.device));
     CK(cudaDeviceSynchronize());
-    unsigned long long h[8];
+    unsigned long long h[16];
     CK(cudaMemcpy(h, e->stats, sizeof h, cudaMemcpyDeviceToHost));
     CK(cudaMemset(e->stats, 0, sizeof h));
+#ifdef AZG_TREE_PROF
+    fprintf(stderr, "tree step sections (cycles summed over warps): load %llu backup %llu select %llu insert %llu expand+store %llu | per-WG total %llu over %llu warpgroups | "
+            "discrete level loop: scores %llu draw+pick %llu next row %llu over %llu warp-levels\n", h[8], h[9], h[10], h[11], h[12], h[0], h[4], h[13], h[14], h[11], h[15]);
+#endif
     for (int k = 0; k < 8; ++k) out[k] = (int64_t)h[k];
     return AZG_OK;
 }

@@ -289,9 +289,11 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
     // per-tree counters: read here, written at the end (a read-modify-write at the end exposed the load latency)
     uint32_t ctr_levels = 0, ctr_scanned = 0;
     if (SELECT) { ctr_levels = p.ctr[t]; ctr_scanned = p.ctr[(size_t)p.B + t]; }
+    TP_BEGIN();
     CCtl c = load_ctl(p.ctl, p.BS, t);
     uint32_t pathw[4];
     memcpy(pathw, c.path, 16);
+    TP_STAMP(0);
     if (BACKUP) {
         // backprop (mcts.py:241-267) along the recorded path.  leafR already holds r_leaf + gamma*V_leaf
         // (the f32 product of NEP 50, added by the evaluation kernel's epilogue).
@@ -307,6 +309,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
         }
         if (d > 0) c.root_nn += 1;  // root.n
     }
+    TP_STAMP(1);
 
     if (SELECT) {
         const int64_t tree = tree_base(p) + t;
@@ -343,6 +346,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
             nk = (int)(kw[3] >> 24);
             cur_th = s1.th; cur_thdot = s1.thdot;
         }
+        TP_STAMP(2);
         if (nan) { atomicOr(p.err, ERR_NAN); kind = KIND_ERROR; }
         if (kind == KIND_INSERT && (n_rows >= p.R || n_rows >= 255 || nk >= (cur == 0 ? CROOT_MAX_KIDS : CROW_MAX_KIDS))) {
             atomicOr(p.err, ERR_CAPACITY);
@@ -368,6 +372,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
             if (depth < 16) set_list_byte(pathw, depth, sel); else path_ovf[depth] = (uint8_t)sel;
             ++depth;
         }
+        TP_STAMP(3);
         if (kind == KIND_INSERT || kind == KIND_EXPAND) {
             if (parent_is_root) {  // the root's state sits in row 0 (read only when the tree grows at the root)
                 const CSec1 s0 = load_sec1(rows);
@@ -409,6 +414,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
     }
     memcpy(c.path, pathw, 16);
     store_ctl(p.ctl, p.BS, t, c);
+    TP_STAMP(4);
 }
 template <bool BACKUP, bool SELECT>
 __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {

@@ -61,6 +61,7 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
     DRow* rows = p.drows + (size_t)t * p.R;
 
     uint16_t* path = p.dpath + (size_t)t * p.R;
+    TP_BEGIN();
     if (BACKUP) {
         // R = leaf.V; up the path: R = node.r + gamma*R; edge.n += 1; edge.W += R; parent.n += 1 (mcts.py:241-267).
         // The select step recorded the path (row, action) root -> leaf, so the row addresses are known up front and the rows are
@@ -98,6 +99,7 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
         }
     }
 
+    TP_STAMP(1);
     if (SELECT) {
         const int64_t tree = tree_base(p) + t;
         int draws = p.draws[t];
@@ -131,6 +133,10 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
                 u[i] = Q + pc * div_small(sq, n + 1, tb.rcp, tb.n);
             }
             nan |= (u[0] != u[0]) || (u[1] != u[1]);
+#ifdef AZG_TREE_PROF
+            if (u[0] + u[1] == 12345.678) atomicOr(p.err, 0);  // (profiling builds: the scores are complete before the stamp)
+            TP_STAMP(5);
+#endif
             bool random_pick = false;
             if (p.epsilon != 0 && p.rng_mt) {
                 random_pick = mt_random_dev(mt, mti, draws) < p.epsilon;
@@ -156,6 +162,11 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
                 else a = u[1] > u[0] ? 1 : 0;
                 ++draws;
             }
+#ifdef AZG_TREE_PROF
+            if (a == 77) atomicOr(p.err, 0);
+            TP_STAMP(6);
+            if ((threadIdx.x & 31) == 0 && p.prof) atomicAdd(p.prof + 7, 1ull);
+#endif
             path[levels] = (uint16_t)((cur << 1) | a);
             ++levels;
             const int child = a ? c1 : c0;
@@ -167,7 +178,12 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
                 for (int q = 0; q < 4; ++q) d[q] = a ? k1[q] : k0[q];
             }
             if (row.flags & ROW_TERMINAL) { a = -1; break; }  // trace ends on an existing terminal node
+#ifdef AZG_TREE_PROF
+            if (row.node_n == -77) atomicOr(p.err, 0);  // (the next row has arrived)
+            TP_STAMP(3);
+#endif
         }
+        TP_STAMP(2);
         if (nan) atomicOr(p.err, ERR_NAN);
         if (p.rng_mt) mt[MT_N] = (uint32_t)mti;
         p.ddepth[t] = (int)levels;  // edges between the root and the leaf (the new node, or the existing terminal node the trace ended on)
@@ -210,6 +226,7 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
             p.leaf[t] = cur;
             p.ctr[(size_t)2 * p.B + t] += 1;
         }
+        TP_STAMP(4);
     }
 }
 

@@ -140,14 +140,17 @@ class SearchEngine:
                 check(self._lib.azg_search_continuous(self._h, B, _ptr(root_state), n_rollouts, tree_id0, self._stream()))
         self.last_B = B
 
-    def root_results(self, B: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    def root_results(self, B: Optional[int] = None, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """return_results of every tree as device tensors; `out` (a dict from an earlier call) is overwritten in place if given."""
         B = B or self.last_B
         dev = self.device
-        out = dict(actions=torch.empty((B, self.cmax), dtype=torch.float32, device=dev),
-                   counts=torch.empty((B, self.cmax), dtype=torch.int32, device=dev),
-                   Q=torch.empty((B, self.cmax), dtype=torch.float64, device=dev),
-                   V_target=torch.empty(B, dtype=torch.float64, device=dev),
-                   n_children=torch.empty(B, dtype=torch.int32, device=dev))
+        if out is None:
+            out = dict(actions=torch.empty((B, self.cmax), dtype=torch.float32, device=dev),
+                       counts=torch.empty((B, self.cmax), dtype=torch.int32, device=dev),
+                       Q=torch.empty((B, self.cmax), dtype=torch.float64, device=dev),
+                       V_target=torch.empty(B, dtype=torch.float64, device=dev),
+                       n_children=torch.empty(B, dtype=torch.int32, device=dev))
+        assert out["actions"].shape == (B, self.cmax) and out["Q"].dtype == torch.float64
         with torch.cuda.device(dev):
             check(self._lib.azg_root_results(self._h, B, _ptr(out["actions"]), _ptr(out["counts"]), _ptr(out["Q"]),
                                              _ptr(out["V_target"]), _ptr(out["n_children"]), self._stream()))

@@ -7,23 +7,28 @@
 
 A "step" is one full batched search over one batch of synthetic roots: root evaluation, n_rollouts
 simulations (backup + select + env step + leaf evaluation) and root-result extraction.
-Workload (default, BASELINE.json configs[3]): 65536 Pendulum-v0 trees per GPU x 100
+Headline workload (BASELINE.json configs[3]): 65536 Pendulum-v0 trees per GPU x 100
 simulations, progressive widening, GMM K=2 policy, MLP 3-128-128-128 ELU, default-initialised weights
 (torch.manual_seed(34)), roots from numpy default_rng(34).  Trees are independent, so N GPUs run N shards
 with no data-path collective (weak scaling: 65536 trees per GPU).
 
-One JSON line on stdout:
+One JSON line on stdout.  Top level = the headline workload:
   value      whole-job sims/s, roots already resident in HBM, results left on the device (CUDA events)
-  e2e        the same through the host-buffer C-ABI call azg_search_host: pinned H2D of the roots and D2H of
+  e2e        the same through the host-buffer C-ABI calls: pinned H2D of the roots and D2H of
              (actions, counts, Q, V_target, n_children) inside the timed region
-  roofline   for the dominant kernel, from per-launch CUDA-event times taken live (azg_profile_search)
+  roofline   for the dominant kernel, times taken live with CUDA events; `traffic` measured in this run (ncu, 2 metrics)
   cpu_baseline  the CPU oracle (a C port of the reference search) on a bounded sample of the same workload
-`--impl reference` times that CPU port alone (the reference itself is Python + gym and cannot travel to the
+  parity     every rank checks a sample of its own trees against the CPU oracle, bit for bit
+Without --workload the line also carries
+  workloads  {cartpole_4096x50 (configs[2]), selfplay_pendulum_32768x200 (configs[4])}: the same record for each
+  strong     (N > 1) the headline workload with the 65536 trees SPLIT over the N GPUs (BASELINE config 4 as worded)
+`--impl reference` times the CPU port alone (the reference itself is Python + gym and cannot travel to the
 GPU box; its single-core numbers measured in the build container are in BASELINE.md / DESIGN.md).
 """
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import statistics
@@ -48,8 +53,25 @@ WORKLOADS = {
     "selfplay_pendulum_32768x200": ("continuous", 32768, 200),
     "selfplay_pendulum_2048x25": ("continuous", 2048, 25),  # quick sanity size
 }
+
+
+class _Workloads(dict):
+    """Named BASELINE configs plus any `pendulum_<trees>x<sims>` / `cartpole_<trees>x<sims>` size (sweeps, strong-scaling shards)."""
+
+    def __missing__(self, name):
+        import re
+        m = re.fullmatch(r"(selfplay_)?(pendulum|cartpole)_(\d+)x(\d+)", name)
+        if not m:
+            raise KeyError(name)
+        return ("continuous" if m.group(2) == "pendulum" else "discrete", int(m.group(3)), int(m.group(4)))
+
+
+WORKLOADS = _Workloads(WORKLOADS)
+HEADLINE = "pendulum_65536x100"
+EXTRA_WORKLOADS = ("cartpole_4096x50", "selfplay_pendulum_32768x200")
 SELFPLAY_BROADCAST_EVERY = 4
 FLOP_PER_EVAL = {"discrete": 2 * 17280, "continuous": 2 * 34048}  # SURVEY 8d
+PARITY_SAMPLE = 256  # trees per rank compared with the oracle inside the bench
 
 
 def make_roots(variant: str, B: int, seed: int = 34) -> np.ndarray:
@@ -77,11 +99,13 @@ def engine_config(variant: str, B: int, N: int, device: int, q8: bool = False, f
                         device=device, seed=34, eval_q8=q8, fused=fused)
 
 
-def oracle_config(variant: str, N: int):
+def oracle_config(variant: str, N: int, q8: bool = False):
     from oracle import azo
-    if variant == "discrete":
-        return azo.discrete_config(n_rollouts=N, epsilon=0.1, math_mode=azo.MATH_DET)
-    return azo.continuous_config(n_rollouts=N, math_mode=azo.MATH_DET)
+    cfg = (azo.discrete_config(n_rollouts=N, epsilon=0.1, math_mode=azo.MATH_DET) if variant == "discrete"
+           else azo.continuous_config(n_rollouts=N, math_mode=azo.MATH_DET))
+    if q8:
+        cfg.eval_mode = azo.EVAL_Q8
+    return cfg
 
 
 class ClockSampler:
@@ -150,6 +174,30 @@ def algorithmic_bytes(variant: str, c: dict) -> float:
     return c["levels"] * (12 + 44) + c["children_scanned"] * per_child + expansions * exp_bytes
 
 
+def measure_traffic(workload: str):
+    """DRAM bytes (read + write) of ONE launch of the whole-search kernel, measured now: a two-metric ncu pass over
+    tools/ncu_one.py (same workload, same library).  Returns (bytes or None, how)."""
+    ncu = "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:k_search_wg|k_qmlp2",
+           "-s", "2", "-c", "1", "--csv", sys.executable, os.path.join(ROOT, "tools", "ncu_one.py"), workload]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
+        total = 0.0
+        for row in csv.reader(l for l in out.splitlines() if l.startswith('"')):
+            if len(row) > 14 and row[12].startswith("dram__bytes_") and row[12].endswith(".sum"):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row[13])
+                if scale is None:
+                    return None, f"unknown ncu unit {row[13]}"
+                total += float(row[14].replace(",", "")) * scale
+        if total > 0:
+            return total, "ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch, measured in this run"
+        return None, "ncu gave no counters (permissions?)"
+    except Exception as exc:  # noqa: BLE001
+        return None, f"ncu failed: {exc}"
+
+
 def cpu_port_throughput(variant: str, N: int, roots: np.ndarray, weights: np.ndarray, seconds: float, threads: int):
     """Time the CPU oracle (C port of the reference search) on a bounded sample; returns (sims/s, sample text)."""
     from oracle import azo
@@ -193,7 +241,7 @@ def run_reference(args, variant, B, N, rank, world):
     line = {"impl": "reference", "metric": "MCTS simulations/sec (batched trees)", "value": v, "unit": "sims/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 tree statistics / f32 network", "data": "synthetic",
-            "config": {"workload": args.workload, "trees_per_step": n, "n_rollouts": N,
+            "config": {"workload": args.workload or HEADLINE, "trees_per_step": n, "n_rollouts": N,
                        "note": "CPU C port (oracle/azg_oracle.c) of the reference's python search; the python reference cannot travel"},
             "cpu_baseline": {"value": v, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -218,59 +266,61 @@ def _emit(line: dict) -> None:
     print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
 
 
-def main():
-    _claim_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pendulum_65536x100", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fused", default="auto", choices=["auto", "on", "off"],
-                    help="whole-search persistent kernel (AZG_FLAG_FUSED); auto = the engine's default")
-    ap.add_argument("--eval", default="q8", choices=["fp32", "q8"],
-                    help="leaf evaluation arithmetic: int8-sliced tcgen05 products (qmlp2.cuh, default) or FP32 FMA (mlp.cuh)")
-    args = ap.parse_args()
-    variant, B, N = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+class Ctx:
+    """One process per GPU: rank / world / local device and the barrier + max-over-ranks reduction of the timing contract."""
 
-    if args.impl == "reference":
-        run_reference(args, variant, B, N, rank, world)
-        return
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            # stdout carries the one JSON line and nothing else: NCCL's own log (its version banner under NCCL_DEBUG=VERSION/INFO) goes to stderr
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
 
-    import torch
-    import torch.distributed as dist
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measure(ctx: Ctx, args, name: str, trees_per_gpu=None, scaling: str = "weak", cpu_baseline: bool = True, traffic: bool = True) -> dict:
+    """One workload on every rank; returns the record (meaningful on rank 0)."""
+    torch, dist = ctx.torch, ctx.dist
     from alphazero_gym_b200.engine import SearchEngine
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        # stdout carries the one JSON line and nothing else: NCCL's own log (its version banner under NCCL_DEBUG=VERSION/INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    variant, B_full, N = WORKLOADS[name]
+    B = int(trees_per_gpu or B_full)
+    rank, world, local = ctx.rank, ctx.world, ctx.local
+    q8 = args.eval == "q8"
     tree_id0 = rank * B  # global tree ids: shard r owns trees [r*B, (r+1)*B)
     roots_h = make_roots(variant, B * world)[rank * B:(rank + 1) * B].copy()
     weights = make_weights(variant)
-    eng = SearchEngine(engine_config(variant, B, N, local, q8=args.eval == "q8", fused={"auto": None, "on": True, "off": False}[args.fused]))
+    eng = SearchEngine(engine_config(variant, B, N, local, q8=q8, fused={"auto": None, "on": True, "off": False}[args.fused]))
     eng.set_weights(weights)
     roots_d = torch.from_numpy(roots_h).cuda()
-
-    selfplay = args.workload.startswith("selfplay")
-    api = "azg_search_host via SearchEngine.search_host, page-locked host buffers (wall clock between syncs)"
+    selfplay = name.startswith("selfplay")
+    sp_times = {}
+    e2e_blocking_s = None
     if selfplay:
         # ---- self-play loop (BASELINE config 5): search -> final action -> real env step, replay rows all-gathered every
-        # step (C2), weights re-broadcast from rank 0 and re-loaded every SELFPLAY_BROADCAST_EVERY steps (C1)
+        # step (C2: ONE all_gather_into_tensor of the packed row buffer), weights re-broadcast from rank 0 and re-loaded every
+        # SELFPLAY_BROADCAST_EVERY steps (C1)
         from alphazero_gym_b200.selfplay import DeviceReplayBuffer, ROW_KEYS, SelfPlayDriver
         drv = SelfPlayDriver(eng, B, N, max_episode_length=200, tree_id0=tree_id0, total_envs=B * world, seed=34)
         replay = DeviceReplayBuffer(max_size=2 * B * world, batch_size=256, obs_dim=3 if variant == "continuous" else 4,
@@ -278,12 +328,23 @@ def main():
         wflat = torch.from_numpy(weights).cuda()
         w_pinned = torch.from_numpy(weights).pin_memory()
         rows_pinned = {k: torch.empty_like(drv.t[k], device="cpu").pin_memory() for k in ROW_KEYS}
+        ev_pairs = {"allgather": [], "broadcast": []}
 
-        def device_step(i):
+        def timed(kind, fn, record):
+            if not record:
+                return fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            ev_pairs[kind].append((a, b))
+            return out
+
+        def device_step(i, record=False):
             if i % SELFPLAY_BROADCAST_EVERY == 0:
-                drv.sync_weights(wflat)
+                timed("broadcast", lambda: drv.sync_weights(wflat), record)
             drv.step(store=False)
-            replay.store(drv.gathered_rows())
+            replay.store(timed("allgather", drv.gathered_rows, record))
 
         def host_step(i):
             if i % SELFPLAY_BROADCAST_EVERY == 0:
@@ -300,9 +361,11 @@ def main():
         d2h = sum(rows_pinned[k].numel() * rows_pinned[k].element_size() for k in ROW_KEYS)
         extra_launches = 2  # root results + the self-play kernel (+ set_seed)
     else:
-        def device_step(i):
+        res_d = eng.root_results(B)  # result tensors allocated once (a cudaMalloc inside the timed loop synchronises the device)
+
+        def device_step(i, record=False):
             eng.search(roots_d, N, tree_id0=tree_id0)
-            return eng.root_results()
+            return eng.root_results(B, out=res_d)
 
         host_out = eng.host_buffers(B)  # page-locked, as the contract asks: results arrive by DMA, no staging copy
         roots_pinned = torch.from_numpy(roots_h).pin_memory().numpy()
@@ -332,37 +395,56 @@ def main():
         device_step(i)
     eng.status()
     clocks = ClockSampler(local)
-    barrier()
+    ctx.barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        device_step(i)
+        res = device_step(i, record=True)
     e1.record()
-    barrier()
+    ctx.barrier()
     ms = e0.elapsed_time(e1)
     eng.status()
     counters = eng.counters()
     launches_per_step = counters["launches"] + extra_launches
+    if selfplay:
+        sp_times = {k: (sum(a.elapsed_time(b) for a, b in v) / max(1, len(v)), len(v)) for k, v in ev_pairs.items()}
+
+    # ---- parity inside the bench: a sample of THIS rank's trees against the CPU oracle, bit for bit -------------------
+    parity = None
+    if not selfplay and q8:
+        from oracle import azo
+        n = min(PARITY_SAMPLE, B)
+        ref = azo.search(oracle_config(variant, N, q8=True), weights, roots_h[:n], tree_id0=tree_id0, dump=False, n_threads=os.cpu_count() or 1)
+        c = ref["counts"].shape[1]
+        same = all(np.array_equal(res[k][:n].cpu().numpy()[:, :c] if res[k].dim() == 2 else res[k][:n].cpu().numpy(), ref[k])
+                   for k in ("counts", "actions", "Q", "V_target", "n_children"))
+        assert same, f"rank {rank}: root results of the first {n} trees differ from the CPU oracle"
+        flag = torch.tensor([1.0 if same else 0.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity = {"trees_per_rank": n, "ranks": world, "bit_identical_to_oracle": bool(flag.item() == 1.0),
+                  "compared": "counts, actions, Q, V_target, n_children of each rank's first trees (global tree ids rank*B ...)"}
 
     # ---- end to end through the host-facing entry point ("e2e") -------------------------------------
     for i in range(2):
         out = host_step(i)
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         out = host_step(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_blocking_s = None
-    if not selfplay:  # the pipelined entry points: the number reported as e2e; the blocking call's stays next to it
+    if selfplay:
+        api_s = api
+    else:  # the pipelined entry points: the number reported as e2e; the blocking call's stays next to it
         host_pipeline(2)
-        barrier()
+        ctx.barrier()
         t0 = time.perf_counter()
         out = host_pipeline(args.steps)
         e2e_blocking_s, e2e_s = e2e_s, time.perf_counter() - t0
-        api = ("azg_search_host_begin / azg_search_host_end via SearchEngine.search_host_begin / _end, two searches in flight, page-locked "
-               "host buffers (wall clock from the first begin to the last end); blocking_value = azg_search_host, one call per step")
+        api_s = ("azg_search_host_begin / azg_search_host_end via SearchEngine.search_host_begin / _end, two searches in flight, page-locked "
+                 "host buffers (wall clock from the first begin to the last end); blocking_value = azg_search_host, one call per step")
     clk = clocks.stop()
     checksum = int(drv.t["counts"].sum()) if selfplay else int(out["counts"].sum())
     assert checksum == B * N, f"visit counts do not add up: {checksum} != {B * N}"
@@ -371,52 +453,13 @@ def main():
     else:
         d2h = sum(out[k].nbytes for k in ("actions", "counts", "Q", "V_target", "n_children"))
 
-    # ---- per-kernel times, live, for the roofline ----------------------------------------------------
-    eng.profile_search(roots_d, N, tree_id0=tree_id0)
-    prof = eng.profile_search(roots_d, N, tree_id0=tree_id0)
-    pc = eng.counters()
+    # ---- roofline of the dominant kernel, timed live ----------------------------------------------------
     hbm_peak, sm_max_mhz, bf16_peak, peak_src = measured_peaks()
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
-    ev, tr = prof["evaluation"], prof["tree_step"]
     fp32_peak = sm_count * 128 * 2 * sm_max_mhz * 1e6 / 1e12
-    ev_avg_ms = ev["ms"] / max(1, ev["launches"])
-    tr_avg_ms = tr["ms"] / max(1, tr["launches"])
-    ev_tflops = FLOP_PER_EVAL[variant] * B / (ev_avg_ms * 1e-3) / 1e12
-    tr_bytes = algorithmic_bytes(variant, pc) / max(1, tr["launches"])
-    tr_gbs = tr_bytes / (tr_avg_ms * 1e-3) / 1e9
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get(args.workload, {})
-    ev_share = ev["ms"] / (ev["ms"] + tr["ms"] + prof["setup"]["ms"])
-    if args.eval == "q8":
-        # tensor-core evaluation: algorithmic FLOPs (2 x MACs of the network) against the measured dense bf16 peak.
-        # The exact fixed-point arithmetic issues 6 int8 MMAs per algorithmic H x H product, and the kernel is bound by its
-        # CUDA-core epilogue (dequantise, activation, quantise), not by the tensor pipe -- DESIGN.md section 4.2.
-        hh = 2 * 128 * 128 * ((3 if variant == "continuous" else 2) - 1)
-        roof_eval = {"kernel": "k_qmlp2 (leaf evaluation, tcgen05 kind::i8)", "bound": "tensor", "achieved": ev_tflops, "peak": bf16_peak,
-                     "unit": "TFLOP/s", "frac": ev_tflops / bf16_peak, "traffic": traffic.get("k_qmlp2"),
-                     "peak_source": peak_src + " dense bf16; int8 digits: 6 MMAs per algorithmic product",
-                     "avg_launch_ms": ev_avg_ms, "launches": ev["launches"], "flop_per_launch": FLOP_PER_EVAL[variant] * B,
-                     "tensor_ops_issued_per_launch": 6 * hh * B, "tensor_tops_issued": 6 * hh * B / (ev_avg_ms * 1e-3) / 1e12,
-                     "frac_of_fp32_cuda_core_peak": ev_tflops / fp32_peak, "share_of_step": ev_share}
-    else:
-        roof_eval = {"kernel": "k_mlp (leaf evaluation)", "bound": "fp32", "achieved": ev_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                     "frac": ev_tflops / fp32_peak, "traffic": traffic.get("k_mlp"),
-                     "peak_source": f"{sm_count} SMs x 128 FMA/clk x 2 x {sm_max_mhz:.0f} MHz (CUDA-core FP32)",
-                     "avg_launch_ms": ev_avg_ms, "launches": ev["launches"], "flop_per_launch": FLOP_PER_EVAL[variant] * B,
-                     "share_of_step": ev_share}
-    roof_tree = {"kernel": "k_step (backup + select + expansion/env step)", "bound": "hbm", "achieved": tr_gbs, "peak": hbm_peak,
-                 "unit": "GB/s", "frac": tr_gbs / hbm_peak, "traffic": traffic.get("k_step"), "peak_source": peak_src,
-                 "avg_launch_ms": tr_avg_ms, "launches": tr["launches"], "algorithmic_bytes_per_launch": tr_bytes,
-                 "algorithmic_bytes_per_sim": algorithmic_bytes(variant, pc) / max(1, pc["sims"]),
-                 "share_of_step": tr["ms"] / (ev["ms"] + tr["ms"] + prof["setup"]["ms"])}
-    dominant = roof_eval if ev["ms"] >= tr["ms"] else roof_tree
-    roof_all = {"evaluation": roof_eval, "tree_step": roof_tree}
+    roof_all = {}
     if eng.cfg.is_fused():
-        # The search runs as ONE persistent kernel (AZG_FLAG_FUSED); the per-kernel numbers above are those of the same search as one
-        # launch per kernel and simulation (azg_profile_search always takes that path) and stay in roofline_all for comparison.
+        # the search is ONE persistent launch per chunk of trees (search_wg.cuh): CUDA events around back-to-back launches
         eng.fused_stats()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = max(3, args.steps)
@@ -430,31 +473,56 @@ def main():
         fc = eng.counters()
         flop = FLOP_PER_EVAL[variant] * fc["evals"] / max(1, counters["launches"])
         tflops = flop / (k_ms * 1e-3) / 1e12
-        ev_ms, tree_ms = k_ms * (1.0 - st["tree_phase"]), k_ms * st["tree_phase"]
         tbytes = algorithmic_bytes(variant, fc) / max(1, counters["launches"])
         hh = 2 * 128 * 128 * ((3 if variant == "continuous" else 2) - 1)
+        tr_bytes, tr_how = (measure_traffic(name) if (traffic and rank == 0 and world == 1 and not selfplay) else (None, "not measured for this record"))
+        if tr_bytes is None:
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    tr_bytes = json.load(f).get(name, {}).get("k_search")
+                tr_how += "; value from profiles/traffic.json (an earlier ncu capture)" if tr_bytes else ""
+        tree_s, slot_s, mma_s = st["tree_phase"], st["wait_for_post_processing"], st.get("x_wait_mma", 0.0)
         dominant = {
-            "kernel": "k_qmlp2<FUSED> (whole search in one persistent kernel: per simulation an evaluation phase on tcgen05 kind::i8 "
-                      "and a tree phase, backup + select + expansion, one thread per tree)",
+            "kernel": "k_search_wg (whole search in one persistent kernel; four independent warpgroups per SM, a thread owns its tree's step "
+                      "and its row of the tcgen05 kind::i8 evaluation)",
             "bound": "tensor", "achieved": tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tflops / bf16_peak,
-            "traffic": traffic.get("k_search"), "peak_source": peak_src + " dense bf16; int8 digits: 6 MMAs per algorithmic product",
+            "traffic": tr_bytes, "traffic_source": tr_how, "peak_source": peak_src + " dense bf16; int8 digits: 6 digit products per algorithmic product",
             "avg_launch_ms": k_ms, "launches": counters["launches"], "flop_per_launch": flop,
             "tensor_tops_issued": 6 * hh * fc["evals"] / max(1, counters["launches"]) / (k_ms * 1e-3) / 1e12,
-            "frac_of_fp32_cuda_core_peak": tflops / fp32_peak, "share_of_step": 1.0,
-            "phases": {
-                "evaluation": {"share": 1.0 - st["tree_phase"], "ms_per_launch": ev_ms, "tflops_in_phase": flop / (ev_ms * 1e-3) / 1e12,
-                               "frac_of_tensor_peak_in_phase": flop / (ev_ms * 1e-3) / 1e12 / bf16_peak,
-                               "frac_of_fp32_cuda_core_peak_in_phase": flop / (ev_ms * 1e-3) / 1e12 / fp32_peak},
-                "tree": {"share": st["tree_phase"], "ms_per_launch": tree_ms, "algorithmic_bytes_per_launch": tbytes,
-                         "hbm_gbs_in_phase": tbytes / (tree_ms * 1e-3) / 1e9, "frac_of_hbm_peak_in_phase": tbytes / (tree_ms * 1e-3) / 1e9 / hbm_peak,
-                         "bound": "dependent-load latency chain + L1 tag lookups of per-thread scattered accesses (profiles/README.md r1f/r1g)"},
-                "source": "in-kernel cycle counters (azg_fused_stats)"},
+            "frac_of_fp32_cuda_core_peak": tflops / fp32_peak, "share_of_step": k_ms * counters["launches"] / (ms / args.steps) if not selfplay else None,
+            "hbm": {"algorithmic_bytes_per_launch": tbytes, "algorithmic_gbs": tbytes / (k_ms * 1e-3) / 1e9,
+                    "frac_of_hbm_peak": tbytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                    "traffic_over_algorithmic": (tr_bytes / tbytes) if tr_bytes else None,
+                    "note": "select + backup + expansion bytes (SURVEY 8d formula from the engine's own counters) over the WHOLE kernel's time: "
+                            "the tree step overlaps the evaluation of other warpgroups, so it has no time of its own"},
+            "warpgroup_time": {"evaluation_with_tmem_slot": 1.0 - tree_s - slot_s, "of_which_waiting_for_mma": mma_s, "tree_step_and_row_finish": tree_s,
+                               "waiting_for_a_tmem_slot": slot_s, "source": "in-kernel cycle counters (azg_fused_stats), average over warpgroups"},
         }
-        roof_all = {"whole_search_kernel": dominant, "per_simulation_launches": {"evaluation": roof_eval, "tree_step": roof_tree}}
+        roof_all = {"whole_search_kernel": dominant}
+    else:
+        eng.profile_search(roots_d, N, tree_id0=tree_id0)
+        prof = eng.profile_search(roots_d, N, tree_id0=tree_id0)
+        pc = eng.counters()
+        ev, tr = prof["evaluation"], prof["tree_step"]
+        ev_avg_ms, tr_avg_ms = ev["ms"] / max(1, ev["launches"]), tr["ms"] / max(1, tr["launches"])
+        ev_tflops = FLOP_PER_EVAL[variant] * B / (ev_avg_ms * 1e-3) / 1e12
+        tr_bytes = algorithmic_bytes(variant, pc) / max(1, tr["launches"])
+        tr_gbs = tr_bytes / (tr_avg_ms * 1e-3) / 1e9
+        tot = ev["ms"] + tr["ms"] + prof["setup"]["ms"]
+        roof_eval = {"kernel": "k_qmlp2 (tcgen05 kind::i8)" if q8 else "k_mlp (FP32 FMA)", "bound": "tensor" if q8 else "fp32", "achieved": ev_tflops,
+                     "peak": bf16_peak if q8 else fp32_peak, "unit": "TFLOP/s", "frac": ev_tflops / (bf16_peak if q8 else fp32_peak), "traffic": None,
+                     "avg_launch_ms": ev_avg_ms, "launches": ev["launches"], "share_of_step": ev["ms"] / tot}
+        roof_tree = {"kernel": "k_step (backup + select + expansion/env step)", "bound": "hbm", "achieved": tr_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": tr_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": tr_avg_ms, "launches": tr["launches"],
+                     "algorithmic_bytes_per_launch": tr_bytes, "share_of_step": tr["ms"] / tot}
+        dominant = roof_eval if ev["ms"] >= tr["ms"] else roof_tree
+        roof_all = {"evaluation": roof_eval, "tree_step": roof_tree}
+        fc = pc
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if cpu_baseline and rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, sample = cpu_port_throughput(variant, N, roots_h, weights, args.cpu_seconds, threads)
         if selfplay:
@@ -462,40 +530,79 @@ def main():
         cpu = {"value": v, "unit": "sims/s", "cores": threads, "kind": "port", "sample": sample}
 
     # ---- max over ranks ---------------------------------------------------------------------------------------
-    t = torch.tensor([ms, e2e_s * 1e3, (e2e_blocking_s or 0.0) * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, e2e_blocking_ms_max = float(t[0]), float(t[1]), float(t[2])
+    ms_max, e2e_ms_max, e2e_blocking_ms_max = ctx.max_over_ranks([ms, e2e_s * 1e3, (e2e_blocking_s or 0.0) * 1e3])
     total_sims = world * B * N * args.steps
-    if rank == 0:
-        line = {
-            "metric": "MCTS simulations/sec (batched trees)", "value": total_sims / (ms_max * 1e-3), "unit": "sims/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 tree statistics + env dynamics / " + ("f32 network with exact int8-sliced tensor-core products" if args.eval == "q8" else "f32 network"),
-            "data": "synthetic",
-            "config": {"workload": args.workload, "eval": args.eval, "whole_search_kernel": bool(eng.cfg.is_fused()), "env": "Pendulum-v0" if variant == "continuous" else "CartPole-v0",
-                       "trees_per_gpu": B, "global_trees": B * world, "n_rollouts": N, "parallelism": f"tree-sharded x{world}, no data-path collective",
-                       "weights": "default init, torch.manual_seed(34)", "roots": "numpy default_rng(34)",
-                       "l2": "node tables per GPU (%.0f MB) exceed the 126 MB L2; no explicit flush" % (eng.rows * B * (32 + 16 + 32) / 1e6)
-                       if variant == "continuous" else "tables are L2-resident at this size (SURVEY 8d config 3); no explicit flush"},
-            "e2e": {"value": total_sims / (e2e_ms_max * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_max / args.steps, "api": api,
-                    **({"blocking_value": total_sims / (e2e_blocking_ms_max * 1e-3)} if e2e_blocking_ms_max > 0 else {})},
-            "gpu_launches": launches_per_step * args.steps,
-            **({"selfplay": {"max_episode_length": 200, "weight_broadcast_every_steps": SELFPLAY_BROADCAST_EVERY,
-                             "collectives_per_step": "all_gather of 5 replay-row tensors (C2); broadcast of the flat weights every k steps (C1)",
-                             "backend": "nccl" if world > 1 else "none (1 GPU)"}} if selfplay else {}),
-            "clocks": clk,
-            "roofline": dominant,
-            "roofline_all": roof_all,
-            "counters_per_sim": {k: pc[k] / max(1, pc["sims"]) for k in ("levels", "children_scanned", "pw_inserts", "evals")},
-            "cpu_baseline": cpu,
-        }
-        _emit(line)
+    rec = {
+        "workload": name, "value": total_sims / (ms_max * 1e-3), "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "scaling": scaling,
+        "config": {"workload": name, "eval": args.eval, "whole_search_kernel": bool(eng.cfg.is_fused()),
+                   "env": "Pendulum-v0" if variant == "continuous" else "CartPole-v0",
+                   "trees_per_gpu": B, "global_trees": B * world, "n_rollouts": N,
+                   "parallelism": f"tree-sharded x{world}, no data-path collective" + (" in the search; C1 + C2 around it" if selfplay else ""),
+                   "weights": "default init, torch.manual_seed(34)", "roots": "numpy default_rng(34)",
+                   "l2": ("node tables per GPU (%.0f MB) exceed the 126 MB L2; no explicit flush" % (eng.rows * B * (64 + 32) / 1e6))
+                   if eng.rows * B * 96 > 126e6 else "tables are L2-resident at this size; no explicit flush (SURVEY 8d says so for config 3)"},
+        "e2e": {"value": total_sims / (e2e_ms_max * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_max / args.steps, "api": api_s,
+                **({"blocking_value": total_sims / (e2e_blocking_ms_max * 1e-3)} if e2e_blocking_ms_max > 0 else {})},
+        "gpu_launches": launches_per_step * args.steps,
+        **({"selfplay": {"max_episode_length": 200, "weight_broadcast_every_steps": SELFPLAY_BROADCAST_EVERY,
+                         "collectives": "C2 = ONE all_gather_into_tensor of the packed replay-row buffer per step (%d B per rank); "
+                                        "C1 = broadcast of the flat f32 weights (%d B) every %d steps" % (drv.packed.nbytes, weights.nbytes, SELFPLAY_BROADCAST_EVERY),
+                         "allgather_ms_per_step": sp_times.get("allgather", (None, 0))[0], "broadcast_plus_set_weights_ms": sp_times.get("broadcast", (None, 0))[0],
+                         "backend": "nccl" if world > 1 else "none (1 GPU: the gather is the identity)"}} if selfplay else {}),
+        "clocks": clk, "roofline": dominant, "roofline_all": roof_all,
+        "counters_per_sim": {k: fc[k] / max(1, fc["sims"]) for k in ("levels", "children_scanned", "pw_inserts", "evals")},
+        "cpu_baseline": cpu, "parity": parity,
+    }
     eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return rec
+
+
+def main():
+    _claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None,
+                    help="one workload only: %s or any pendulum_<trees>x<sims> / cartpole_<trees>x<sims> "
+                         "(default: the headline workload + the other BASELINE configs under `workloads`)" % ", ".join(sorted(WORKLOADS)))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only: no `workloads`, no `strong` record")
+    ap.add_argument("--fused", default="auto", choices=["auto", "on", "off"],
+                    help="whole-search persistent kernel (AZG_FLAG_FUSED); auto = the engine's default")
+    ap.add_argument("--eval", default="q8", choices=["fp32", "q8"],
+                    help="leaf evaluation arithmetic: int8-sliced tcgen05 products (default) or FP32 FMA (mlp.cuh)")
+    args = ap.parse_args()
+    head = args.workload or HEADLINE
+    variant, B, N = WORKLOADS[head]
+    if args.impl == "reference":
+        run_reference(args, variant, B, N, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+        return
+    ctx = Ctx()
+    rec = measure(ctx, args, head)
+    extras, strong = {}, None
+    if args.workload is None and not args.no_extra:
+        for name in EXTRA_WORKLOADS:
+            extras[name] = measure(ctx, args, name, traffic=False)
+        if ctx.world > 1 and B % ctx.world == 0:
+            # BASELINE config 4 as worded: the SAME 65536 trees sharded B / N per GPU (parallel.shard_range): strong scaling
+            strong = measure(ctx, args, head, trees_per_gpu=B // ctx.world, scaling="strong", cpu_baseline=False, traffic=False)
+    if ctx.rank == 0:
+        line = {"metric": "MCTS simulations/sec (batched trees)", "higher_is_better": True, "vs_baseline": None,
+                "dtype": "f64 tree statistics + env dynamics / " + ("f32 network with exact int8-sliced tensor-core products" if args.eval == "q8" else "f32 network"),
+                "data": "synthetic"}
+        line.update({k: v for k, v in rec.items() if k != "workload"})
+        if extras:
+            line["workloads"] = extras
+        if strong is not None:
+            line["strong"] = {k: strong[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "parity", "clocks")}
+            line["strong"]["roofline_frac"] = strong["roofline"]["frac"]
+        _emit(line)
+    ctx.close()
 
 
 if __name__ == "__main__":
