@@ -42,7 +42,10 @@ class EngineConfig:
     log_std_max: float = 2.0
     seed: int = 34
     use_graph: bool = True
-    eval_q8: bool = False  # AZG_FLAG_EVAL_Q8: hidden x hidden layers on tcgen05 as exact int8-sliced products (include/azg.h)
+    # AZG_FLAG_EVAL_Q8: hidden x hidden layers on tcgen05 as exact int8-sliced products (include/azg.h).  None = on wherever the
+    # tensor-core kernel serves the network (hidden 128, 2 or 3 hidden layers, at most 15 head outputs): the drop-in classes, the
+    # self-play driver and bench.py all run the same evaluation; False selects the FP32 FMA kernel (mlp.cuh)
+    eval_q8: Optional[bool] = None
     rng_mt19937: bool = False  # AZG_FLAG_RNG_MT19937: CPython's generator for the discrete search's selection draws (include/azg.h)
     fused: Optional[bool] = None  # AZG_FLAG_FUSED: whole search in one persistent kernel; None = on where supported (eval_q8)
 
@@ -51,11 +54,18 @@ class EngineConfig:
                          self.state_dim, self.hidden, self.n_hidden, self.activation, VT[self.V_target_policy],
                          self.puct_f32, self.device, self.c_uct, float(self.gamma), self.epsilon, self.c_pw, self.kappa,
                          self.action_bound, self.log_std_min, self.log_std_max,
-                         (0 if self.use_graph else _cabi.FLAG_NO_GRAPH) | (_cabi.FLAG_EVAL_Q8 if self.eval_q8 else 0)
+                         (0 if self.use_graph else _cabi.FLAG_NO_GRAPH) | (_cabi.FLAG_EVAL_Q8 if self.is_q8() else 0)
                          | (_cabi.FLAG_FUSED if self.is_fused() else 0) | (_cabi.FLAG_RNG_MT19937 if self.rng_mt19937 else 0), self.seed)
 
+    def q8_supported(self) -> bool:
+        head = self.num_actions if self.variant == DISCRETE else (3 * self.num_components if self.num_components > 1 else 2)
+        return self.hidden == 128 and self.n_hidden in (2, 3) and 1 + head <= 16
+
+    def is_q8(self) -> bool:
+        return self.q8_supported() if self.eval_q8 is None else bool(self.eval_q8)
+
     def is_fused(self) -> bool:
-        supported = bool(self.eval_q8) and self.state_dim == (3 if self.variant == CONTINUOUS else 4)
+        supported = self.is_q8() and self.state_dim == (3 if self.variant == CONTINUOUS else 4)
         return supported if self.fused is None else bool(self.fused)
 
 

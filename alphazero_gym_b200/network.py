@@ -76,6 +76,27 @@ class PolicyNet(nn.Module):
         return self
 
 
+def make_policy(representation_dim: int, action_dim: int, distribution: str, hidden_dimensions, nonlinearity: str,
+                num_components: int = None, num_actions: int = None, action_bound: float = None, layernorm: bool = False,
+                log_param_min: float = -5, log_param_max: float = 2) -> PolicyNet:
+    """Same keyword arguments as the reference's `make_policy` (alphazero/network/policies.py:806-916, the `_target_` of
+    config/policy/*.yaml); returns a PolicyNet with the reference's parameter layout (discrete / squashed Normal / GMM heads)."""
+    if layernorm:
+        raise NotImplementedError("layernorm=True policies are not supported by the CUDA evaluation kernel")
+    if len(set(hidden_dimensions)) != 1:
+        raise NotImplementedError("all hidden layers must have the same width")
+    if distribution == "discrete":
+        return PolicyNet(representation_dim, hidden_dimensions[0], len(hidden_dimensions), num_actions, nonlinearity, num_actions=num_actions)
+    if distribution == "beta":
+        raise NotImplementedError("GeneralizedBetaPolicy is declared broken upstream (README.md:21-22) and is not implemented")
+    if distribution != "normal" or action_dim != 1:
+        raise NotImplementedError("continuous policies: distribution 'normal' with action_dim 1 (Pendulum)")
+    K = int(num_components or 1)
+    return PolicyNet(representation_dim, hidden_dimensions[0], len(hidden_dimensions), policy_head_dim("continuous", num_components=K),
+                     nonlinearity, num_components=K, action_bound=float(action_bound or 0.0), log_param_min=log_param_min,
+                     log_param_max=log_param_max)
+
+
 def describe_model(model) -> dict:
     """Network shape the engine needs, read off a reference-style policy module (policies.py:806 make_policy
     products or PolicyNet): trunk widths, activation, head size, mixture components, log-std clamp."""

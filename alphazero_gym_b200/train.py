@@ -183,7 +183,8 @@ class Trainer:
         self.device = next(net.parameters()).device
         self.cuda_graph = bool(cuda_graph) and self.device.type == "cuda"
         self.loss = A0CLoss(loss, self.device, capturable=self.cuda_graph)
-        self.opt = make_optimizer(optimizer, net.parameters(), lr, capturable=self.cuda_graph)
+        # `optimizer`: "rmsprop" / "adam" (the reference's two configs) or an already constructed torch optimizer over net.parameters()
+        self.opt = make_optimizer(optimizer, net.parameters(), lr, capturable=self.cuda_graph) if isinstance(optimizer, str) else optimizer
         self.clip = grad_clip
         self.discrete = bool(net.num_actions)
         self.n_root_actions = n_root_actions

@@ -559,6 +559,56 @@ def measure(ctx: Ctx, args, name: str, trees_per_gpu=None, scaling: str = "weak"
     return rec
 
 
+class _CartPoleEnv:  # what the drop-in classes read of a gym env: the class name and the hidden state (search/mcts.py env_hidden_state)
+    def __init__(self, state):
+        self.state, self.unwrapped = np.asarray(state, np.float64), self
+
+
+class _PendulumEnv(_CartPoleEnv):
+    pass
+
+
+def single_tree_latency(searches: int = 200) -> dict:
+    """BASELINE configs[0] and configs[1]: ONE tree through the reference-facing drop-in call `MCTS*.search(Env)` +
+    `return_results` (run_discrete.yaml / run_continuous.yaml defaults: 8 / 25 rollouts), host buffers in and out, and the CPU
+    port on one core next to it.  (The Python reference itself measured 1431 / 935 sims/s on one core of the build container.)"""
+    import torch
+    from oracle import azo
+    from alphazero_gym_b200.network import PolicyNet
+    from alphazero_gym_b200.search.mcts import MCTSContinuous, MCTSDiscrete
+    out = {}
+    for name, variant, N in (("cartpole_1x8", "discrete", 8), ("pendulum_1x25", "continuous", 25)):
+        w, roots = make_weights(variant), make_roots(variant, searches)
+        if variant == "discrete":
+            net = PolicyNet(4, 128, 2, 2, "relu", num_actions=2).load_flat(w)
+            m = MCTSDiscrete(model=net, num_actions=2, n_rollouts=N, c_uct=1.5, gamma=1, epsilon=0.1, V_target_policy="off_policy", device="cuda:0", root_state=None)
+            envs = [_CartPoleEnv(r) for r in roots]
+        else:
+            net = PolicyNet(3, 128, 3, 6, "elu", num_components=2, action_bound=2.0).load_flat(w)
+            m = MCTSContinuous(model=net, n_rollouts=N, c_uct=0.05, c_pw=1, kappa=0.5, gamma=1, epsilon=0, V_target_policy="off_policy", device="cuda:0", root_state=None)
+            envs = [_PendulumEnv(r) for r in roots]
+        for e in envs[:10]:
+            m.root_node, m.root_state = None, None
+            m.search(Env=e)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for e in envs:
+            m.root_node, m.root_state = None, None  # reset_mcts (agents.py:146-155)
+            m.search(Env=e)
+            m.return_results("max_visit")
+        dt = time.perf_counter() - t0
+        m.close()
+        cfg = oracle_config(variant, N)
+        t0 = time.perf_counter()
+        for i in range(searches):
+            azo.search(cfg, w, roots[i:i + 1], dump=False, n_threads=1, tree_id0=i)
+        dc = time.perf_counter() - t0
+        out[name] = {"ms_per_search": 1e3 * dt / searches, "sims_per_s": searches * N / dt, "searches": searches,
+                     "api": "MCTSDiscrete/MCTSContinuous.search(Env) + return_results (drop-in classes, tensor-core evaluation, one launch per search)",
+                     "cpu_port_one_core": {"ms_per_search": 1e3 * dc / searches, "sims_per_s": searches * N / dc}}
+    return out
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -598,6 +648,8 @@ def main():
         line.update({k: v for k, v in rec.items() if k != "workload"})
         if extras:
             line["workloads"] = extras
+        if args.workload is None and not args.no_extra and ctx.world == 1:
+            line["single_tree"] = single_tree_latency()
         if strong is not None:
             line["strong"] = {k: strong[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "parity", "clocks")}
             line["strong"]["roofline_frac"] = strong["roofline"]["frac"]

@@ -22,14 +22,18 @@ def _model(cfg, weights):
     return net.load_flat(weights)
 
 
-@pytest.mark.parametrize("name", ["cartpole_n8_eps01", "cartpole_n50_eps0", "cartpole_n50_onpolicy_g099"])
-def test_mcts_discrete_dropin(name):
+@pytest.mark.parametrize("eval_q8", [None, False])  # None: the default = tensor-core evaluation (what bench.py times); False: FP32 FMA
+@pytest.mark.parametrize("name", ["cartpole_n8_eps01", "cartpole_n50_eps0", "cartpole_n50_onpolicy_g099", "cartpole_n50_trained"])
+def test_mcts_discrete_dropin(name, eval_q8):
     from alphazero_gym_b200.search.mcts import MCTSDiscrete
     cfg, g = G.load(name)
+    cfg.eval_mode = azo.EVAL_FP32 if eval_q8 is False else azo.EVAL_Q8
     model = _model(cfg, g["weights"])
     env = CartPoleEnv(g["root_state"][0])
     mcts = MCTSDiscrete(model=model, num_actions=2, n_rollouts=cfg.n_rollouts, c_uct=cfg.c_uct, gamma=cfg.gamma, epsilon=cfg.epsilon,
-                        V_target_policy=cfg.V_target_policy, device="cuda:0", root_state=np.array(env.state), seed=cfg.seed)
+                        V_target_policy=cfg.V_target_policy, device="cuda:0", root_state=np.array(env.state), seed=cfg.seed,
+                        **({} if eval_q8 is None else {"eval_q8": eval_q8}))
+    assert mcts._engine(1).cfg.is_q8() == (eval_q8 is None)
     mcts.search(Env=env)
     state, actions, counts, Q, V = mcts.return_results("max_visit")
     # first search of the object uses tree id 0 == tree 0 of the golden batch
@@ -47,6 +51,7 @@ def test_mcts_discrete_forward_reuses_root_count():
     """forward() keeps only root.n; the next search equals the oracle run with that root_n_init."""
     from alphazero_gym_b200.search.mcts import MCTSDiscrete
     cfg, g = G.load("cartpole_n16_reuse")
+    cfg.eval_mode = azo.EVAL_Q8  # the drop-in classes run the tensor-core evaluation by default
     model = _model(cfg, g["weights"])
     roots = G.cartpole_roots(8)
     env = CartPoleEnv(roots[0])
@@ -95,9 +100,10 @@ def test_agents_act_and_weight_refresh():
     from alphazero_gym_b200.agent.agents import ContinuousAgent, DiscreteAgent
     from alphazero_gym_b200.search.mcts import MCTSContinuous, MCTSDiscrete
     cfg, g = G.load("pendulum_n25_k2")
+    cfg.eval_mode = azo.EVAL_Q8
     model = _model(cfg, g["weights"])
     env = PendulumEnv(g["root_state"][1])
-    agent = ContinuousAgent(model, MCTSContinuous(model=model, n_rollouts=25, c_uct=0.05, c_pw=1, kappa=0.5, gamma=1, epsilon=0,
+    agent = ContinuousAgent.from_modules(model, MCTSContinuous(model=model, n_rollouts=25, c_uct=0.05, c_pw=1, kappa=0.5, gamma=1, epsilon=0,
                                                   V_target_policy="off_policy", device="cuda:0", root_state=None, seed=cfg.seed))
     agent.reset_mcts(root_state=env.obs())
     action, state, actions, counts, Qs, V = agent.act(env)
@@ -117,7 +123,7 @@ def test_agents_act_and_weight_refresh():
     dcfg, dg = G.load("cartpole_n8_eps01")
     dmodel = _model(dcfg, dg["weights"])
     denv = CartPoleEnv(dg["root_state"][0])
-    dagent = DiscreteAgent(dmodel, MCTSDiscrete(model=dmodel, num_actions=2, n_rollouts=8, c_uct=1.5, gamma=1, epsilon=0.1,
+    dagent = DiscreteAgent.from_modules(dmodel, MCTSDiscrete(model=dmodel, num_actions=2, n_rollouts=8, c_uct=1.5, gamma=1, epsilon=0.1,
                                                 V_target_policy="off_policy", device="cuda:0", root_state=np.array(denv.state)))
     np.random.seed(0)
     for _ in range(5):  # the run_discrete.py loop shape: act -> env.step -> mcts_forward
