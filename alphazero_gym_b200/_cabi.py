@@ -13,7 +13,9 @@ LIB_PATH = os.environ.get("AZG_LIB_PATH") or os.path.join(HERE, "lib", "libazg.s
 
 AZG_OK, AZG_EINVAL, AZG_ECUDA, AZG_ETERMINAL, AZG_ENAN, AZG_ECAPACITY = 0, -1, -2, -3, -4, -5
 DISCRETE, CONTINUOUS = 0, 1
-ACT_RELU, ACT_ELU = 0, 1
+ACT_RELU, ACT_ELU, ACT_LEAKYRELU, ACT_RELU6, ACT_SILU, ACT_HARDSWISH = 0, 1, 2, 3, 4, 5
+# nonlinearity strings of config/policy/*.yaml (alphazero/network/utils.py:5-14) and torch module names -> AZG_ACT_*
+ACT_BY_NAME = {"relu": 0, "elu": 1, "leakyrelu": 2, "relu6": 3, "swish": 4, "silu": 4, "hardswish": 5}
 VT = {"off_policy": 0, "on_policy": 1, "greedy": 2}
 FLAG_NO_GRAPH = 1
 FLAG_EVAL_Q8 = 2

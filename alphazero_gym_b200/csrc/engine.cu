@@ -164,7 +164,9 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     if (c.max_rollouts < 1 || c.max_trees < 1) return fail(AZG_EINVAL, "max_rollouts and max_trees must be >= 1");
     if (c.hidden != 128 && c.hidden != 64) return fail(AZG_EINVAL, "hidden width must be 64 or 128 (weights are staged in shared memory)");
     if (c.n_hidden < 1 || c.n_hidden > 4) return fail(AZG_EINVAL, "n_hidden must be in 1..4");
-    if (c.activation != AZG_ACT_RELU && c.activation != AZG_ACT_ELU) return fail(AZG_EINVAL, "activation must be relu or elu");
+    if (c.activation < AZG_ACT_RELU || c.activation > AZG_ACT_HARDSWISH) return fail(AZG_EINVAL, "activation must be one of AZG_ACT_*");
+    if ((c.flags & AZG_FLAG_EVAL_Q8) && c.activation > AZG_ACT_ELU)
+        return fail(AZG_EINVAL, "AZG_FLAG_EVAL_Q8 serves relu and elu (the configured activations); the others run on the FP32 kernel");
     if (c.variant == AZG_DISCRETE) {
         if (c.num_actions != 2 || c.state_dim != 4)
             return fail(AZG_EINVAL, "discrete variant is CartPole: num_actions must be 2 and state_dim 4");
@@ -617,6 +619,10 @@ static cudaError_t launch_mlp(const azg_engine* e, const MlpParams& m, cudaStrea
     if (H == h && S == s && A == a) return launch_mlp_t<h, s, a>(e, m, st, set_attr);
     MLP_CASE(128, 4, 0) MLP_CASE(128, 4, 1) MLP_CASE(128, 3, 0) MLP_CASE(128, 3, 1)
     MLP_CASE(64, 4, 0) MLP_CASE(64, 4, 1) MLP_CASE(64, 3, 0) MLP_CASE(64, 3, 1)
+    MLP_CASE(128, 4, 2) MLP_CASE(128, 4, 3) MLP_CASE(128, 4, 4) MLP_CASE(128, 4, 5)
+    MLP_CASE(128, 3, 2) MLP_CASE(128, 3, 3) MLP_CASE(128, 3, 4) MLP_CASE(128, 3, 5)
+    MLP_CASE(64, 4, 2) MLP_CASE(64, 4, 3) MLP_CASE(64, 4, 4) MLP_CASE(64, 4, 5)
+    MLP_CASE(64, 3, 2) MLP_CASE(64, 3, 3) MLP_CASE(64, 3, 4) MLP_CASE(64, 3, 5)
 #undef MLP_CASE
     return cudaErrorInvalidValue;
 }

@@ -102,8 +102,18 @@ __device__ __forceinline__ float mlp_pow2_of_magic(float tm) {  // tm = t + MAGI
     return __uint_as_float((__float_as_uint(tm) << 23) + 0x3F800000u);
 }
 
+// the activations of the reference's map beyond ReLU / ELU (alphazero/network/utils.py:5-14), each the scalar f32 operation
+// sequence of the torch CPU kernel it replaces; SiLU through the deterministic expf (<= 1 ulp from torch's)
+__device__ __forceinline__ float mlp_act_other(int act, float v) {
+    if (act == 2) return v > 0.0f ? v : __fmul_rn(v, 0.01f);                                     // LeakyReLU(0.01)
+    if (act == 3) return fminf(fmaxf(v, 0.0f), 6.0f);                                             // ReLU6
+    if (act == 4) return (v != v) ? v : __fdiv_rn(v, __fadd_rn(1.0f, det::expf_(-v)));            // SiLU: x / (1 + exp(-x))
+    return __fdiv_rn(__fmul_rn(v, fminf(fmaxf(__fadd_rn(v, 3.0f), 0.0f), 6.0f)), 6.0f);           // Hardswish: x * relu6(x + 3) / 6
+}
+
 template <int ACT>
 __device__ __forceinline__ float mlp_act(float v) {
+    if (ACT >= 2) return mlp_act_other(ACT, v);
     if (ACT == 0) return v > 0.0f ? v : 0.0f;  // ReLU (DiscretePolicy.yaml:8)
     // ELU alpha=1 (ContinuousPolicy.yaml:9): v > 0 ? v : expm1(v), expm1 = det::expm1f_ written with selects.
     // (n == 0 needs no special case: fma(p, 1, 0) == p; for v > 0 the exponential branch is computed on garbage and discarded.)
@@ -126,6 +136,7 @@ __device__ __forceinline__ float mlp_act(float v) {
 // IEEE operation, so results are bit-identical to mlp_act on each element)
 template <int ACT>
 __device__ __forceinline__ float2 mlp_act2(float2 v) {
+    if (ACT >= 2) return make_float2(mlp_act_other(ACT, v.x), mlp_act_other(ACT, v.y));
     if (ACT == 0) return make_float2(v.x > 0.0f ? v.x : 0.0f, v.y > 0.0f ? v.y : 0.0f);
     const float2 xx = make_float2(fmaxf(v.x, -20.0f), fmaxf(v.y, -20.0f));
     const float2 magic = make_float2(MLP_RINT_MAGIC, MLP_RINT_MAGIC);

@@ -59,7 +59,7 @@ class EngineConfig:
 
     def q8_supported(self) -> bool:
         head = self.num_actions if self.variant == DISCRETE else (3 * self.num_components if self.num_components > 1 else 2)
-        return self.hidden == 128 and self.n_hidden in (2, 3) and 1 + head <= 16
+        return self.hidden == 128 and self.n_hidden in (2, 3) and 1 + head <= 16 and self.activation in (ACT_RELU, ACT_ELU)
 
     def is_q8(self) -> bool:
         return self.q8_supported() if self.eval_q8 is None else bool(self.eval_q8)

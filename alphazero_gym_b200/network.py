@@ -53,7 +53,8 @@ class PolicyNet(nn.Module):
                  num_components: int = 1, num_actions: int = 0, action_bound: float = 2.0,
                  log_param_min: float = -5.0, log_param_max: float = 2.0):
         super().__init__()
-        act = {"relu": nn.ReLU, "elu": nn.ELU}[nonlinearity.lower()]
+        act = {"relu": nn.ReLU, "elu": nn.ELU, "leakyrelu": nn.LeakyReLU, "relu6": nn.ReLU6, "swish": nn.SiLU, "silu": nn.SiLU,
+               "hardswish": nn.Hardswish}[nonlinearity.lower()]  # the reference's map (alphazero/network/utils.py:5-14)
         layers, d = [], state_dim
         for _ in range(n_hidden):
             layers += [nn.Linear(d, hidden), act()]
@@ -115,10 +116,11 @@ def describe_model(model) -> dict:
     for k in tw:
         if sd[k].shape[0] != hidden:
             raise NotImplementedError("all hidden layers must have the same width")
+    from ._cabi import ACT_BY_NAME
     act_name = type(model.trunk[1]).__name__.lower()
-    if act_name not in ("relu", "elu"):
-        raise NotImplementedError(f"activation {act_name} is not supported (relu / elu are the configured ones)")
-    return dict(state_dim=sd[tw[0]].shape[1], hidden=hidden, n_hidden=len(tw), activation=0 if act_name == "relu" else 1,
+    if act_name not in ACT_BY_NAME:
+        raise NotImplementedError(f"activation {act_name} is not in the reference's map (alphazero/network/utils.py:5-14)")
+    return dict(state_dim=sd[tw[0]].shape[1], hidden=hidden, n_hidden=len(tw), activation=ACT_BY_NAME[act_name],
                 head_dim=sd["dist_head.weight"].shape[0], num_components=int(getattr(model, "num_components", 1) or 1),
                 action_bound=float(getattr(model, "action_bound", None) or 0.0),
                 log_std_min=float(getattr(model, "log_param_min", -5.0)), log_std_max=float(getattr(model, "log_param_max", 2.0)))

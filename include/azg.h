@@ -35,6 +35,11 @@ extern "C" {
 
 #define AZG_ACT_RELU 0
 #define AZG_ACT_ELU 1
+/* the other entries of the reference's activation map (alphazero/network/utils.py:5-14); FP32 evaluation kernel only */
+#define AZG_ACT_LEAKYRELU 2 /* nn.LeakyReLU(): x > 0 ? x : 0.01 x */
+#define AZG_ACT_RELU6 3     /* nn.ReLU6() */
+#define AZG_ACT_SILU 4      /* nn.SiLU(), config names "swish" and "silu" */
+#define AZG_ACT_HARDSWISH 5 /* nn.Hardswish() */
 
 #define AZG_VT_OFF_POLICY 0 /* mcts.py:131 */
 #define AZG_VT_ON_POLICY 1  /* mcts.py:111 */

@@ -327,6 +327,19 @@ static void net_free(net_t* n) {
 
 static inline float act_fn(const azo_config* c, float v) {
     if (c->activation == AZO_ACT_RELU) return v > 0.0f ? v : 0.0f;
+    if (c->activation == AZO_ACT_LEAKYRELU) return v > 0.0f ? v : v * 0.01f;
+    if (c->activation == AZO_ACT_RELU6) return fminf(fmaxf(v, 0.0f), 6.0f);
+    if (c->activation == AZO_ACT_SILU) {
+        if (v != v) return v;
+        const float e = c->math_mode == AZO_MATH_DET ? azo_det_expf(-v) : expf(-v);
+        volatile float d = 1.0f + e;
+        return v / d;
+    }
+    if (c->activation == AZO_ACT_HARDSWISH) {
+        volatile float t = v + 3.0f;
+        volatile float m = v * fminf(fmaxf(t, 0.0f), 6.0f);
+        return m / 6.0f;
+    }
     /* ELU alpha=1 (ContinuousPolicy.yaml:9): x > 0 ? x : expm1(x) */
     if (v > 0.0f) return v;
     return c->math_mode == AZO_MATH_DET ? azo_det_expm1f(v) : expm1f(v);

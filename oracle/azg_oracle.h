@@ -45,6 +45,10 @@ extern "C" {
 
 #define AZO_ACT_RELU 0
 #define AZO_ACT_ELU 1
+#define AZO_ACT_LEAKYRELU 2 /* nn.LeakyReLU(): x > 0 ? x : 0.01 x   (network/utils.py:5-14) */
+#define AZO_ACT_RELU6 3     /* nn.ReLU6(): min(max(x, 0), 6) */
+#define AZO_ACT_SILU 4      /* nn.SiLU() ("swish" / "silu"): x / (1 + exp(-x)) */
+#define AZO_ACT_HARDSWISH 5 /* nn.Hardswish(): x * min(max(x + 3, 0), 6) / 6 */
 
 #define AZO_MATH_LIBM 0 /* glibc sin/cos/expf/... : what the python reference calls */
 #define AZO_MATH_DET 1  /* op-for-op deterministic functions shared (as a spec) with the CUDA engine */

@@ -17,7 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libazg_oracle.so")
 
 DISCRETE, CONTINUOUS = 0, 1
-ACT_RELU, ACT_ELU = 0, 1
+ACT_RELU, ACT_ELU, ACT_LEAKYRELU, ACT_RELU6, ACT_SILU, ACT_HARDSWISH = 0, 1, 2, 3, 4, 5
+ACT_NAMES = {0: "relu", 1: "elu", 2: "leakyrelu", 3: "relu6", 4: "silu", 5: "hardswish"}
 MATH_LIBM, MATH_DET = 0, 1
 EVAL_FP32, EVAL_Q8 = 0, 1
 RNG_PHILOX, RNG_MT19937 = 0, 1

@@ -57,6 +57,11 @@ CASES = {
     # V_target_policy "greedy" (mcts.py:133-173; from a non-terminal root its loop never runs, so it is the root's Q.max())
     "cartpole_n8_greedy": dict(cfg=azo.discrete_config(n_rollouts=8, epsilon=0.1, V_target_policy="greedy"), B=8),
     "pendulum_n25_greedy": dict(cfg=azo.continuous_config(n_rollouts=25, V_target_policy="greedy"), B=6),
+    # the rest of the reference's activation map (alphazero/network/utils.py:5-14): leakyrelu, relu6, swish / silu, hardswish
+    "cartpole_n8_leakyrelu": dict(cfg=azo.discrete_config(n_rollouts=8, epsilon=0.1, activation=azo.ACT_LEAKYRELU), B=8),
+    "cartpole_n8_hardswish": dict(cfg=azo.discrete_config(n_rollouts=8, epsilon=0.1, activation=azo.ACT_HARDSWISH), B=8),
+    "pendulum_n25_relu6": dict(cfg=azo.continuous_config(n_rollouts=25, activation=azo.ACT_RELU6), B=6),
+    "pendulum_n25_silu": dict(cfg=azo.continuous_config(n_rollouts=25, activation=azo.ACT_SILU), B=6),
     # TRAINED weights: the reference agent after 80 real `update` steps (agents.py:319-389, :539-603; lr 3e-3 so that the activation
     # range moves well away from the default initialisation), then its search -- the case the per-row block exponent of the
     # tensor-core evaluation has to survive

@@ -215,7 +215,7 @@ def make_model(cfg: azo.Config, weight_seed: int = 34):
     _, P = reference_modules()
     torch.manual_seed(weight_seed)
     hidden = [cfg.hidden] * cfg.n_hidden
-    act = "relu" if cfg.activation == azo.ACT_RELU else "elu"
+    act = azo.ACT_NAMES[cfg.activation]
     if cfg.variant == azo.DISCRETE:
         return P.make_policy(cfg.state_dim, 1, "discrete", hidden, act, num_actions=cfg.num_actions)
     return P.make_policy(cfg.state_dim, 1, "normal", hidden, act, num_components=cfg.num_components,
