@@ -125,7 +125,8 @@ struct TreeParams {
     int32_t* draws;   // selection RNG draw counter (stream 0)
     int32_t* leaf;    // LEAF_* word
     uint8_t* path;    // [B][R] continuous: path entries beyond the 16 held in CCtl
-    uint32_t* mt;     // [B][625] AZG_FLAG_RNG_MT19937 (discrete): per-tree MT19937 state + index word (see mt19937 below)
+    uint32_t* mt;     // [B][625] AZG_FLAG_RNG_MT19937: per-tree MT19937 state + index word of CPython's generator (see mt19937 below)
+    uint32_t* tmt;    // [B][628] AZG_FLAG_RNG_MT19937, continuous: torch's CPU generator (state, index, cached normal lo / hi / valid)
     int32_t rng_mt;
     uint16_t* dpath;  // [B][R] discrete: the current simulation's path, (row << 1 | action) per level, root first (read by the backup)
     int32_t* ddepth;  // [B]    discrete: its length
@@ -291,6 +292,23 @@ __device__ __forceinline__ int mt_below_dev(uint32_t* mt, int& mti, int& draws, 
 
 // global id of the launch's tree 0 (keys every random stream)
 __device__ __forceinline__ int64_t tree_base(const TreeParams& p) { return p.tree_id0 + (p.tree_word ? (int64_t)__ldg(p.seedp + 1) : 0); }
+
+// ---- AZG_FLAG_RNG_MT19937, continuous search: torch's global CPU generator for the action noise, exactly as an UN-WRAPPED
+// `model.sample_action` consumes it after torch.manual_seed(seed + tree) (contract and derivation: oracle/azg_oracle.c
+// torch_sample_action): at::mt19937 seeded by init_genrand; uniform = 53 bits of (out1 << 32 | out2); torch.multinomial(probs, 1) =
+// argmax_k probs_k / (float)(-log1p(-uniform)); normal = Box-Muller on doubles with the sine kept for the next call.
+#define TMT_WORDS (MT_N + 4)  // state, index, cached normal (lo, hi), cache-valid flag
+__device__ __forceinline__ void tmt_seed_dev(uint32_t* mt, uint64_t seed) {
+    mt[0] = (uint32_t)seed;
+    for (int i = 1; i < MT_N; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    mt[MT_N] = MT_N;
+    mt[MT_N + 1] = mt[MT_N + 2] = mt[MT_N + 3] = 0;
+}
+__device__ __forceinline__ double tmt_uniform_dev(uint32_t* mt, int& mti) {
+    int dummy = 0;
+    const uint64_t hi = mt_next_dev(mt, mti, dummy), lo = mt_next_dev(mt, mti, dummy);
+    return (double)(((hi << 32) | lo) & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+}
 
 // stream 0: random.random() / random.choice / random.randint replacements (helpers.py:51, mcts.py:190-192)
 __device__ __forceinline__ uint32_t rng_select_u32(const TreeParams& p, int64_t tree, int draw) {

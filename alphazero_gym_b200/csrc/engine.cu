@@ -59,6 +59,7 @@ struct azg_engine {
     int32_t *pw_table = nullptr, *n_rows = nullptr, *draws = nullptr, *leaf = nullptr;
     uint8_t* path = nullptr;
     uint32_t* mt = nullptr;     // AZG_FLAG_RNG_MT19937: [B][625]
+    uint32_t* tmt = nullptr;    // AZG_FLAG_RNG_MT19937, continuous: torch's generator [B][628]
     uint16_t* dpath = nullptr;  // discrete: recorded path of the current simulation [B][R]
     int32_t* ddepth = nullptr;
     uint32_t* ctr = nullptr;
@@ -139,7 +140,7 @@ extern "C" void azg_destroy(azg_engine* e) {
     cudaSetDevice(e->cfg.device);
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     void* ptrs[] = {e->drows, e->dstate, e->crows, e->hot_block, e->chead, e->pw_table, e->n_rows, e->draws,
-                    e->leaf, e->path, e->dpath, e->ddepth, e->mt, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qdigits_nat, e->qfl, e->r_actions,
+                    e->leaf, e->path, e->dpath, e->ddepth, e->mt, e->tmt, e->ctr, e->X, e->root_state, e->root_n_init, e->err, e->wpack, e->d_seed, e->stats, e->dtab, e->qdigits, e->qdigits_nat, e->qfl, e->r_actions,
                     e->r_counts, e->r_Q, e->r_Vt, e->r_nchild};
     for (void* q : ptrs)
         if (q) cudaFree(q);
@@ -217,11 +218,11 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
             return fail(AZG_EINVAL, "AZG_FLAG_EVAL_Q8 needs hidden = 128, n_hidden in {2, 3}, at most 15 head outputs and an sm_100 device (tcgen05)");
         }
     }
-    if ((c.flags & AZG_FLAG_RNG_MT19937) && c.variant != AZG_DISCRETE) {
-        delete e;
-        return fail(AZG_EINVAL, "AZG_FLAG_RNG_MT19937 serves the discrete search only (the continuous one also draws from torch's generator)");
-    }
     e->fused = (c.flags & AZG_FLAG_FUSED) != 0;
+    if ((c.flags & AZG_FLAG_RNG_MT19937) && c.variant == AZG_CONTINUOUS && e->fused) {
+        delete e;
+        return fail(AZG_EINVAL, "AZG_FLAG_RNG_MT19937 with the continuous search runs one launch per simulation (no AZG_FLAG_FUSED)");
+    }
     if (e->fused && !(e->q8 && c.state_dim == (c.variant == AZG_CONTINUOUS ? 3 : 4))) {
         delete e;
         return fail(AZG_EINVAL, "AZG_FLAG_FUSED needs AZG_FLAG_EVAL_Q8 and the shipped envs (state_dim 3 continuous / 4 discrete)");
@@ -293,6 +294,10 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
         ALLOC(chead, B * R * e->HS);
         ALLOC(pw_table, pwt.size());
         ALLOC(path, B * R);
+        if (c.flags & AZG_FLAG_RNG_MT19937) {  // CPython's and torch's generator per tree
+            ALLOC(mt, B * (MT_N + 1));
+            ALLOC(tmt, B * TMT_WORDS);
+        }
         CK(cudaMemcpy(e->pw_table, pwt.data(), pwt.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CK(cudaMemset(e->chead, 0, B * R * e->HS * sizeof(float)));
     }
@@ -499,7 +504,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.crows = e->crows; p.et = e->et; p.ctl = e->ctl; p.BS = e->cfg.max_trees; p.chead = e->chead;
     p.pw_table = e->pw_table;
     p.rcp_tab = e->dtab; p.sqrt_tab = e->dtab + AZG_TAB + 1;
-    p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path; p.dpath = e->dpath; p.ddepth = e->ddepth; p.mt = e->mt; p.rng_mt = e->mt != nullptr;
+    p.n_rows = e->n_rows; p.draws = e->draws; p.leaf = e->leaf; p.path = e->path; p.dpath = e->dpath; p.ddepth = e->ddepth; p.mt = e->mt; p.tmt = e->tmt; p.rng_mt = e->mt != nullptr;
     p.ctr = e->ctr; p.X = e->X; p.root_state = e->root_state; p.root_n_init = e->root_n_init; p.err = e->err;
     p.tapeV = e->tapeV; p.tapeP = e->tapeP; p.tapeA = e->tapeA;
     p.prof = e->stats + 8;

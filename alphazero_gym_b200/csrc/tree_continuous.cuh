@@ -153,8 +153,50 @@ __device__ __forceinline__ float new_action_k(const TreeParams& p, const float* 
     return p.action_bound > 0.0f ? __fmul_rn(p.action_bound, det::tanhf_(x)) : x;
 }
 
+// AZG_FLAG_RNG_MT19937: the un-wrapped torch sampling (common.cuh tmt_*; same operation sequence as the oracle's torch_sample_action)
+__device__ __forceinline__ double tmt_normal_dev(uint32_t* mt, int& mti) {
+    if (mt[MT_N + 3]) {
+        mt[MT_N + 3] = 0;
+        return __hiloint2double((int)mt[MT_N + 2], (int)mt[MT_N + 1]);
+    }
+    const double u1 = tmt_uniform_dev(mt, mti), u2 = tmt_uniform_dev(mt, mti);
+    const double r = sqrt(2.0 * -det::log_(1.0 - u2));
+    double sn, cs;
+    det::sincos_(6.283185307179586 * u1, sn, cs);
+    const double cached = r * sn;
+    mt[MT_N + 1] = (uint32_t)__double2loint(cached);
+    mt[MT_N + 2] = (uint32_t)__double2hiint(cached);
+    mt[MT_N + 3] = 1;
+    return r * cs;
+}
+__device__ __forceinline__ float new_action_torch(const TreeParams& p, int t, int node) {
+    const float* head = p.chead + ((size_t)t * p.R + node) * p.HS;
+    uint32_t* mt = p.tmt + (size_t)t * TMT_WORDS;
+    int mti = (int)mt[MT_N];
+    const int K = p.K;
+    int k = 0;
+    if (K > 1) {
+        float best = 0.0f;
+        for (int i = 0; i < K; ++i) {
+            const float q = (float)(-det::log_(1.0 - tmt_uniform_dev(mt, mti)));
+            const float w = __fdiv_rn(head[2 * K + i], q);
+            if (i == 0 || w > best) { best = w; k = i; }
+        }
+    }
+    float z = 0.0f;
+    for (int i = 0; i < K; ++i) {
+        const float zi = (float)tmt_normal_dev(mt, mti);
+        if (i == k) z = zi;
+    }
+    mt[MT_N] = (uint32_t)mti;
+    const float x = __fadd_rn(__fmul_rn(z, head[K + k]), head[k]);
+    return p.action_bound > 0.0f ? __fmul_rn(p.action_bound, det::tanhf_(x)) : x;
+}
+
+template <bool MT = false>
 __device__ __forceinline__ float new_action(const TreeParams& p, int t, int node, int row, int j) {
     if (p.use_tape) return p.tapeA[(size_t)t * p.R + row];
+    if (MT) return new_action_torch(p, t, node);
     {
         const float* hptr = p.chead + ((size_t)t * p.R + node) * p.HS;
         const int64_t tree = tree_base(p) + t;
@@ -199,6 +241,11 @@ __device__ __forceinline__ void c_init(const TreeParams& p, int t) {
     c.leaf = 0 | LEAF_EVAL;
     store_ctl(p.ctl, p.BS, t, c);
     for (int k = 0; k < 4; ++k) p.ctr[(size_t)k * p.B + t] = 0;
+    if (p.rng_mt) {  // random.seed(seed + tree); torch.manual_seed(seed + tree)
+        const uint64_t s = __ldg(p.seedp) + (uint64_t)(tree_base(p) + t);
+        mt_seed_dev(p.mt + (size_t)t * (MT_N + 1), s);
+        tmt_seed_dev(p.tmt + (size_t)t * TMT_WORDS, s);
+    }
 }
 __global__ void k_init_continuous(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -206,10 +253,11 @@ __global__ void k_init_continuous(const TreeParams p) {
 }
 
 // the add_pw_action(root) that precedes the rollout loop (mcts.py:673); runs after the root evaluation
+template <bool MT = false>
 __device__ __forceinline__ void c_root_insert(const TreeParams& p, int t) {
     CRow* rows = p.crows + (size_t)t * p.R;
     CCtl c = load_ctl(p.ctl, p.BS, t);
-    const float a = new_action(p, t, 0, 1, 0);
+    const float a = new_action<MT>(p, t, 0, 1, 0);
     store_hot(p.et + t, fresh_hot(0.0, 0.0f, a, 0));  // root child 0
     store_sec1_new(rows + 1, 0.0, 0.0);
     c.root_kids[0] = 1;
@@ -222,7 +270,9 @@ __device__ __forceinline__ void c_root_insert(const TreeParams& p, int t) {
 }
 __global__ void k_root_insert_continuous(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < p.B) c_root_insert(p, t);
+    if (t >= p.B) return;
+    if (p.rng_mt) c_root_insert<true>(p, t);
+    else c_root_insert<false>(p, t);
 }
 
 #define KIND_INSERT 0    // progressive widening: create a new edge below `cur`, then its node
@@ -240,7 +290,7 @@ __device__ __forceinline__ const CHot* child_hot(const CHot* et, int BS, const C
     return is_root ? et + (size_t)j * BS : reinterpret_cast<const CHot*>(rows + list_byte(kw, j));  // et = &table[0][t]
 }
 __device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, int64_t tree, int nk, uint32_t cur_nn, float cur_V, int& draws,
-                                          bool& nan, const CHot* et, const CRow* rows, const uint32_t kw[4], bool is_root) {
+                                          bool& nan, const CHot* et, const CRow* rows, const uint32_t kw[4], bool is_root, uint32_t* mt = nullptr) {
     const double sq = sqrt_small((int)cur_nn + 1, tb.sq, tb.n);
     double best = -CUDART_INF;
     uint32_t win = 0;
@@ -267,6 +317,15 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, i
         }
     }
     bool random_pick = false;
+    if (mt) {  // AZG_FLAG_RNG_MT19937: CPython's generator (random(): two outputs; choice / randint: _randbelow_with_getrandbits)
+        int mti = (int)mt[MT_N];
+        if (p.epsilon != 0) random_pick = mt_random_dev(mt, mti, draws) < p.epsilon;
+        const int nwm = random_pick ? nk : __popc(win);
+        const int pk = nwm > 0 ? mt_below_dev(mt, mti, draws, nwm) : 0;
+        mt[MT_N] = (uint32_t)mti;
+        if (random_pick) return pk;
+        return nwm > 0 ? (int)__fns(win, 0, pk + 1) : 0;
+    }
     if (p.epsilon != 0) {  // epsilon_greedy (mcts.py:175-195)
         const double x = (double)u32_to_unit(rng_select_u32(p, tree, draws++));
         random_pick = x < p.epsilon;
@@ -282,6 +341,9 @@ __device__ __forceinline__ int uct_select(const TreeParams& p, const Tabs& tb, i
 
 // one simulation step of tree t: backup of the previous simulation (BACKUP), then descent + expansion of the next (SELECT).
 // Shared by k_step_continuous (one launch per simulation) and the whole-search kernel k_search_fused (fused.cuh).
+// MT: AZG_FLAG_RNG_MT19937 (CPython's and torch's generators, 5 KB of state per tree in HBM: a compatibility mode that the one-launch-
+// per-simulation kernel alone instantiates; the whole-search kernels are built without it)
+template <bool MT = false>
 __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int t, const bool BACKUP, const bool SELECT) {
     CRow* rows = p.crows + (size_t)t * p.R;
     CHot* et = p.et + t;  // root child j: et[j * BS]
@@ -327,7 +389,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
         while (true) {
             ++levels;
             if (tb.pw[cur_nn] - nk > 0) { kind = KIND_INSERT; break; }  // states.py:252-275
-            jsel = uct_select(p, tb, tree, nk, cur_nn, cur_V, draws, nan, et, rows, kw, cur == 0);
+            jsel = uct_select(p, tb, tree, nk, cur_nn, cur_V, draws, nan, et, rows, kw, cur == 0, MT ? p.mt + (size_t)t * (MT_N + 1) : nullptr);
             sel = list_byte(kw, jsel);
             const CHot sh = load_hot(child_hot(et, p.BS, rows, kw, cur == 0, jsel));  // the line was gathered a moment ago
             // requested together with sh (one round trip instead of two); used only if the descent enters the node
@@ -358,7 +420,7 @@ __device__ __forceinline__ void c_step(const TreeParams& p, const Tabs& tb, int 
         if (kind == KIND_INSERT) {
             // add_pw_action (mcts.py:625-654): the new edge is selected immediately (mcts.py:725-727)
             sel = n_rows++;
-            sel_action = new_action(p, t, cur, sel, pwc++);
+            sel_action = new_action<MT>(p, t, cur, sel, pwc++);
             jsel = nk;
             if (parent_is_root) {
                 set_list_byte(rootk, nk, sel);
@@ -420,7 +482,9 @@ template <bool BACKUP, bool SELECT>
 __global__ void __launch_bounds__(128) k_step_continuous(const TreeParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const Tabs tb = {p.pw_table, p.rcp_tab, p.sqrt_tab, AZG_TAB};
-    if (t < p.B) c_step(p, tb, t, BACKUP, SELECT);
+    if (t >= p.B) return;
+    if (p.rng_mt) c_step<true>(p, tb, t, BACKUP, SELECT);
+    else c_step<false>(p, tb, t, BACKUP, SELECT);
 }
 
 // numpy pairwise summation for n <= 128 (np.sum in get_on_policy_value_target, mcts.py:111)

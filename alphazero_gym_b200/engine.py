@@ -65,7 +65,8 @@ class EngineConfig:
         return self.q8_supported() if self.eval_q8 is None else bool(self.eval_q8)
 
     def is_fused(self) -> bool:
-        supported = self.is_q8() and self.state_dim == (3 if self.variant == CONTINUOUS else 4)
+        supported = (self.is_q8() and self.state_dim == (3 if self.variant == CONTINUOUS else 4)
+                     and not (self.rng_mt19937 and self.variant == CONTINUOUS))  # the torch-generator mode runs one launch per simulation
         return supported if self.fused is None else bool(self.fused)
 
 

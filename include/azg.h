@@ -78,10 +78,16 @@ typedef struct azg_config {
                                 evaluation of the other.  Same arithmetic, same results bit for bit as the per-simulation
                                 launches. */
 
-#define AZG_FLAG_RNG_MT19937 8u /* discrete variant: the tie-break / eps-greedy draws come from CPython's MT19937 (seeded like
-                                   random.seed(seed + global tree id) at the start of every search; random(), choice and randint with
-                                   CPython's algorithms) instead of the Philox streams, so that a reference run with its stock
-                                   `random` module is reproduced bit for bit (helpers.py:50-51, mcts.py:190-192) */
+#define AZG_FLAG_RNG_MT19937 8u /* un-shimmed compatibility: every random number comes from the generators the reference itself uses,
+                                   seeded per tree at the start of every search like random.seed(seed + global tree id) and
+                                   torch.manual_seed(seed + global tree id).  Tie-break / eps-greedy draws: CPython's MT19937
+                                   (init_by_array seeding; random(), choice and randint with CPython's algorithms; helpers.py:50-51,
+                                   mcts.py:190-192).  Continuous variant additionally: the action noise of model.sample_action
+                                   (policies.py:656-669, :488-499) from torch's CPU generator -- mt19937 + 53-bit uniforms, the
+                                   exponential race of torch.multinomial(probs, 1), Box-Muller pairs with the cached sine of
+                                   torch.normal -- so that a reference run with its stock `random` module and un-wrapped torch is
+                                   reproduced (goldens tests/golden/cartpole_mt_*, pendulum_mt_*).  The continuous variant runs
+                                   this mode with one launch per simulation (no AZG_FLAG_FUSED). */
 
 typedef struct azg_engine azg_engine;
 

@@ -549,7 +549,11 @@ int32_t azo_pw_limit(double c_pw, double kappa, int32_t n) { return (int32_t)cei
 /* ------------------------------------------------------------------------------------------------
  * Selection helpers.
  * ---------------------------------------------------------------------------------------------- */
-typedef struct { uint64_t seed; int64_t tree; int64_t draws; int64_t pw; int mt_mode; int mti; uint32_t mt[624]; } rng_t;
+typedef struct {
+    uint64_t seed; int64_t tree; int64_t draws; int64_t pw; int mt_mode; int mti; uint32_t mt[624];
+    /* AZO_RNG_MT19937, continuous search: torch's CPU generator (see torch_sample_action) */
+    int tmti; uint32_t tmt[624]; int tcache_valid; double tcache; int64_t tdraws;
+} rng_t;
 
 static inline uint32_t rng_next(rng_t* g) { return azo_rng_u32(g->seed, g->tree, 0, g->draws++, 0, 0); }
 
@@ -597,6 +601,71 @@ static uint32_t mt_next(rng_t* g) {
     g->draws++;
     return y;
 }
+/* ---- AZO_RNG_MT19937, continuous search: the action noise comes from torch's global CPU generator exactly as an UN-WRAPPED
+ * `model.sample_action` consumes it after `torch.manual_seed(seed + tree)` (policies.py:656-669 / :488-499; measured against
+ * torch 2.11 in the build container, oracle/gen_golden.py "pendulum_mt_*"):
+ *   generator   at::mt19937 seeded with init_genrand((uint32) seed); random64() = (out1 << 32) | out2
+ *   uniform     (random64() & (2^53 - 1)) * 2^-53                                        [uniform_real_distribution<double>]
+ *   multinomial(probs, 1): q_k = (float)(-log1p(-uniform)) for k = 0..K-1, argmax_k of probs_k / q_k   [the n_sample == 1 fast path]
+ *   normal      Box-Muller on doubles: u1, u2 uniform; r = sqrt(-2 log1p(-u2)), theta = 2 pi u1; returns r cos(theta) and CACHES
+ *               r sin(theta) for the next call (the cache lives in the generator, reset by manual_seed)   [normal_distribution<double>]
+ *   torch.normal(mean, std) over K elements = (float) normal, then * std + mean. */
+static uint32_t tmt_next(rng_t* g) {
+    uint32_t* mt = g->tmt;
+    if (g->tmti >= 624) {
+        int kk;
+        uint32_t y;
+        for (kk = 0; kk < 624 - 397; ++kk) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        for (; kk < 623; ++kk) { y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u); }
+        y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        g->tmti = 0;
+    }
+    uint32_t y = mt[g->tmti++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    g->tdraws++;
+    return y;
+}
+static void torch_manual_seed(rng_t* g, uint64_t seed) {
+    mt_init_genrand(g->tmt, (uint32_t)seed);
+    g->tmti = 624; g->tcache_valid = 0; g->tcache = 0.0; g->tdraws = 0;
+}
+static double torch_uniform(rng_t* g) {
+    const uint64_t hi = tmt_next(g), lo = tmt_next(g);
+    return (double)(((hi << 32) | lo) & ((1ULL << 53) - 1)) * (1.0 / 9007199254740992.0);
+}
+static double torch_neglog1m(const azo_config* c, double u) { /* -log1p(-u); 1 - u is exact for a 53-bit u */
+    return c->math_mode == AZO_MATH_DET ? -azo_det_log(1.0 - u) : -log1p(-u);
+}
+static double torch_normal(const azo_config* c, rng_t* g) {
+    if (g->tcache_valid) { g->tcache_valid = 0; return g->tcache; }
+    const double u1 = torch_uniform(g), u2 = torch_uniform(g);
+    const double r = sqrt(2.0 * torch_neglog1m(c, u2)), th = 6.283185307179586 * u1;
+    g->tcache = r * (c->math_mode == AZO_MATH_DET ? azo_det_sin(th) : sin(th));
+    g->tcache_valid = 1;
+    return r * (c->math_mode == AZO_MATH_DET ? azo_det_cos(th) : cos(th));
+}
+static float torch_sample_action(const azo_config* c, const float* head, rng_t* g) {
+    const int K = c->num_components;
+    int k = 0;
+    if (K > 1) {
+        float best = 0.0f;
+        for (int i = 0; i < K; ++i) {
+            const float q = (float)torch_neglog1m(c, torch_uniform(g));
+            const float w = head[2 * K + i] / q;
+            if (i == 0 || w > best) { best = w; k = i; }
+        }
+    }
+    float z = 0.0f;
+    for (int i = 0; i < K; ++i) {
+        const float zi = (float)torch_normal(c, g);
+        if (i == k) z = zi;
+    }
+    float x = z * head[K + k] + head[k];
+    float t = c->math_mode == AZO_MATH_DET ? azo_det_tanhf(x) : tanhf(x);
+    return c->action_bound > 0.0f ? c->action_bound * t : x;
+}
+
 /* random.random() */
 static double rng_random(rng_t* g) {
     if (!g->mt_mode) return (double)u32_to_unit(rng_next(g));
@@ -810,9 +879,14 @@ static int c_add_pw_action(const azo_config* c, const azo_tapes* tp, int64_t b, 
         a = tp->action[b * t->R + row];
         g->pw++;
     } else {
-        float u, z[AZO_MAX_K];
-        azo_noise(g->seed, g->tree, g->pw++, c->num_components, &u, z);
-        a = azo_sample_action(c, t->head + (size_t)node * t->K3, u, z);
+        if (g->mt_mode) {
+            a = torch_sample_action(c, t->head + (size_t)node * t->K3, g);
+            g->pw++;
+        } else {
+            float u, z[AZO_MAX_K];
+            azo_noise(g->seed, g->tree, g->pw++, c->num_components, &u, z);
+            a = azo_sample_action(c, t->head + (size_t)node * t->K3, u, z);
+        }
     }
     t->parent[row] = node; t->action[row] = a; t->eW[row] = 0.0; t->en[row] = 0; t->expanded[row] = 0;
     t->node_n[row] = 0; t->terminal[row] = 0; t->V[row] = 0.0f; t->r[row] = 0.0;
@@ -904,7 +978,10 @@ static void* worker(void* arg) {
         for (int64_t b = b0; b < b1; ++b) {
             rng_t g;
             g.seed = cfg->seed; g.tree = J->tree_id0 + b; g.draws = 0; g.pw = 0; g.mt_mode = cfg->rng_mode == 1; g.mti = 624;
-            if (g.mt_mode) mt_seed(&g, cfg->seed + (uint64_t)(J->tree_id0 + b));
+            if (g.mt_mode) {
+                mt_seed(&g, cfg->seed + (uint64_t)(J->tree_id0 + b));
+                torch_manual_seed(&g, cfg->seed + (uint64_t)(J->tree_id0 + b));
+            }
             int e;
             if (cfg->variant == AZO_DISCRETE) {
                 e = search_discrete_one(cfg, J->net, J->tapes, b, J->root_state + b * 4, J->root_n_init ? J->root_n_init[b] : 0, &dt, &g, J->ctr);

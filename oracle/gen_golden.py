@@ -80,6 +80,12 @@ MT_CASES = {
     "cartpole_mt_n8_eps01": dict(cfg=_mt(azo.discrete_config(n_rollouts=8, epsilon=0.1)), B=16),
     "cartpole_mt_n50_eps0": dict(cfg=_mt(azo.discrete_config(n_rollouts=50, epsilon=0.0)), B=12),
     "cartpole_mt_n200_terminal": dict(cfg=_mt(azo.discrete_config(n_rollouts=200, epsilon=0.1)), B=6, roots="tilted"),
+    # ... and the continuous search with the stock `random` module AND torch's own global generator (torch.manual_seed(seed + tree)
+    # before the search, torch.multinomial / torch.normal un-wrapped): K = 2 (run_continuous.yaml), K = 1 (the squashed Normal), K = 3
+    "pendulum_mt_n25_k2": dict(cfg=_mt(azo.continuous_config(n_rollouts=25)), B=12),
+    "pendulum_mt_n100_k2": dict(cfg=_mt(azo.continuous_config(n_rollouts=100)), B=6),
+    "pendulum_mt_n50_k1_eps": dict(cfg=_mt(azo.continuous_config(n_rollouts=50, num_components=1, epsilon=0.25)), B=8),
+    "pendulum_mt_n30_k3": dict(cfg=_mt(azo.continuous_config(n_rollouts=30, num_components=3)), B=6),
 }
 CASES_ALL = dict(CASES, **MT_CASES)
 

@@ -343,8 +343,11 @@ def run_continuous(cfg: azo.Config, model, root_states: np.ndarray, tree_id0: in
                draws=np.zeros(B, np.int64), pw_inserts=np.zeros(B, np.int64),
                root_state=np.array(root_states, np.float64).reshape(B, 2))
     orig_add = M.MCTSContinuous.add_pw_action
+    mt = cfg.rng_mode == azo.RNG_MT19937
     for b in range(B):
-        rng = PhiloxRandom(cfg.seed, tree_id0 + b)
+        # rng_mode MT19937: the UN-SHIMMED reference -- the stock `random` module seeded like random.seed(seed + tree) and torch's own
+        # global generator seeded like torch.manual_seed(seed + tree) right before the search; nothing of torch is wrapped
+        rng = StockRandom(cfg.seed + tree_id0 + b) if mt else PhiloxRandom(cfg.seed, tree_id0 + b)
         H.random = M.random = rng
         rows = [0]
 
@@ -359,9 +362,14 @@ def run_continuous(cfg: azo.Config, model, root_states: np.ndarray, tree_id0: in
             mcts = M.MCTSContinuous(model=model, n_rollouts=cfg.n_rollouts, c_uct=cfg.c_uct, c_pw=cfg.c_pw,
                                     kappa=cfg.kappa, gamma=_gamma_arg(cfg.gamma), epsilon=cfg.epsilon,
                                     V_target_policy=cfg.V_target_policy, device="cpu", root_state=env.obs())
-            with NoiseInjector(cfg.seed, tree_id0 + b, K) as inj:
+            if mt:
+                torch.manual_seed(cfg.seed + tree_id0 + b)
                 mcts.search(env)
-                out["pw_inserts"][b] = inj.j
+                out["pw_inserts"][b] = rows[0]
+            else:
+                with NoiseInjector(cfg.seed, tree_id0 + b, K) as inj:
+                    mcts.search(env)
+                    out["pw_inserts"][b] = inj.j
             out["draws"][b] = rng.draws
             _dump_continuous(mcts, model, b, out, env, K)
             s, actions, counts, Q, Vt = mcts.return_results("max_visit")
