@@ -28,10 +28,20 @@ from ..network import describe_model, weights_version
 PENDULUM_R_SCALE = 16.2736044  # reference mcts.py:20 (applied inside the engine)
 
 
+# wrappers rl/make_game.py:71-83 puts around the env for the name suffixes -v0n / r / p / s (rl/wrappers.py:44-155): they change the
+# rewards or observations the search sees, and the engine steps the PLAIN CartPole-v0 / Pendulum-v0 dynamics -- searching through them
+# silently would not be the reference's search, so they are refused (the BASELINE configs use the plain envs)
+_REFUSED_WRAPPERS = ("NormalizeWrapper", "ScaleRewardWrapper", "ReparametrizeWrapper", "PILCOWrapper", "ClipRewardWrapper",
+                     "ScaledObservationWrapper")
+
+
 def _unwrap(env):
     e = env
     seen = 0
     while hasattr(e, "env") and e is not getattr(e, "env") and seen < 16:  # gym.Wrapper chain (rl/make_game.py:60-62)
+        if type(e).__name__ in _REFUSED_WRAPPERS:
+            raise NotImplementedError(f"{type(e).__name__} (rl/wrappers.py) changes what the search sees; the CUDA engine implements the plain "
+                                      "CartPole-v0 / Pendulum-v0 envs of run_discrete.yaml / run_continuous.yaml and has no CPU fallback")
         e = e.env
         seen += 1
     return getattr(e, "unwrapped", e)

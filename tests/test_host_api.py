@@ -153,3 +153,26 @@ def test_hydra_yaml_drop_ins_instantiate():
                  else PolicyNet(3, 128, 3, 6, "elu", num_components=2, action_bound=2.0))
         obj = getattr(importlib.import_module(mod), cls)(model=model, **cfg)
         assert obj.n_rollouts == cfg["n_rollouts"] and obj.c_uct == cfg["c_uct"] and obj.gamma == cfg["gamma"]
+
+
+def test_wrapped_envs_are_refused_not_silently_unwrapped():
+    """rl/make_game.py:71-83 wraps the env for the -v0n/r/p/s name suffixes (rl/wrappers.py): the search would see other rewards /
+    observations than the engine's plain dynamics produce, so the drop-in refuses them; a plain TimeLimit-style wrapper is unwrapped."""
+    import numpy as np
+    import pytest
+    from alphazero_gym_b200._cabi import DISCRETE
+    from alphazero_gym_b200.search.mcts import env_hidden_state
+
+    class CartPoleEnv:
+        state = np.zeros(4)
+
+    class TimeLimit:
+        def __init__(self, env):
+            self.env = env
+
+    class ReparametrizeWrapper(TimeLimit):
+        pass
+
+    assert env_hidden_state(TimeLimit(CartPoleEnv()), DISCRETE).shape == (4,)
+    with pytest.raises(NotImplementedError):
+        env_hidden_state(ReparametrizeWrapper(CartPoleEnv()), DISCRETE)
