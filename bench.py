@@ -483,9 +483,18 @@ def measure(ctx: Ctx, args, name: str, trees_per_gpu=None, scaling: str = "weak"
                     tr_bytes = json.load(f).get(name, {}).get("k_search")
                 tr_how += "; value from profiles/traffic.json (an earlier ncu capture)" if tr_bytes else ""
         tree_s, slot_s, mma_s = st["tree_phase"], st["wait_for_post_processing"], st.get("x_wait_mma", 0.0)
+        two_phase = B < 3 * 128 * sm_count and os.environ.get("AZG_FUSED_KERNEL", "")[:1] != "w"  # engine.cu launch_fused_t picks by batch size
+        if os.environ.get("AZG_FUSED_KERNEL", "")[:1] == "t" or os.environ.get("AZG_FUSED_V1"):
+            two_phase = True
+        wg_time = ({"evaluation_phases": 1.0 - tree_s, "tree_phases": tree_s, "evaluation_warps_waiting_for_row_finish": slot_s,
+                    "source": "in-kernel cycle counters (azg_fused_stats), CTA average; the two phases alternate for the whole CTA"} if two_phase else
+                   {"evaluation_with_tmem_slot": 1.0 - tree_s - slot_s, "of_which_waiting_for_mma": mma_s, "tree_step_and_row_finish": tree_s,
+                    "waiting_for_a_tmem_slot": slot_s, "source": "in-kernel cycle counters (azg_fused_stats), average over warpgroups"})
         dominant = {
-            "kernel": "k_search_wg (whole search in one persistent kernel; four independent warpgroups per SM, a thread owns its tree's step "
-                      "and its row of the tcgen05 kind::i8 evaluation)",
+            "kernel": ("k_qmlp2<FUSED> (whole search in one persistent kernel, thin batches: per simulation an evaluation phase on tcgen05 kind::i8 with "
+                       "16 warps per tile pair and a tree phase, one thread per tree)" if two_phase else
+                       "k_search_wg (whole search in one persistent kernel; four independent warpgroups per SM, a thread owns its tree's step "
+                       "and its row of the tcgen05 kind::i8 evaluation)"),
             "bound": "tensor", "achieved": tflops, "peak": bf16_peak, "unit": "TFLOP/s", "frac": tflops / bf16_peak,
             "traffic": tr_bytes, "traffic_source": tr_how, "peak_source": peak_src + " dense bf16; int8 digits: 6 digit products per algorithmic product",
             "avg_launch_ms": k_ms, "launches": counters["launches"], "flop_per_launch": flop,
@@ -496,8 +505,7 @@ def measure(ctx: Ctx, args, name: str, trees_per_gpu=None, scaling: str = "weak"
                     "traffic_over_algorithmic": (tr_bytes / tbytes) if tr_bytes else None,
                     "note": "select + backup + expansion bytes (SURVEY 8d formula from the engine's own counters) over the WHOLE kernel's time: "
                             "the tree step overlaps the evaluation of other warpgroups, so it has no time of its own"},
-            "warpgroup_time": {"evaluation_with_tmem_slot": 1.0 - tree_s - slot_s, "of_which_waiting_for_mma": mma_s, "tree_step_and_row_finish": tree_s,
-                               "waiting_for_a_tmem_slot": slot_s, "source": "in-kernel cycle counters (azg_fused_stats), average over warpgroups"},
+            "time_split": wg_time,
         }
         roof_all = {"whole_search_kernel": dominant}
     else:
