@@ -79,6 +79,8 @@ struct azg_engine {
     float* qfl = nullptr;
     int qfl_count = 0;
     size_t qmlp_smem = 0;
+    size_t smem_optin = 0;
+    size_t tsm_smem_max = 0;        // discrete whole-search kernel with the trees in shared memory (qmlp2.cuh TSM): dynamic shared memory it may use
     bool q8 = false;
     // continuous tree: root edge tables + control blocks in ONE allocation, pinned in L2 (persisting access-policy window on every
     // launch that walks trees): they are touched by every simulation of every tree (37.7 MB at 65536 trees, against 126 MB of L2),
@@ -192,6 +194,7 @@ extern "C" int azg_create(const azg_config* cfg, azg_engine** out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c.device));
     e->sm_count = prop.multiProcessorCount;
+    e->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
     const int H = c.hidden;
     int64_t nw = (int64_t)c.state_dim * H + H;
     for (int l = 1; l < c.n_hidden; ++l) nw += (int64_t)H * H + H;
@@ -556,6 +559,14 @@ static cudaError_t launch_qmlp_t(const azg_engine* e, const MlpParams& m, cudaSt
         if (ce != cudaSuccess) return ce;
         ce = cudaFuncSetAttribute(k_qmlp2<S, ACT, NL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->qmlp_smem);
         if (ce != cudaSuccess) return ce;
+        if constexpr (S == 4) {  // trees in shared memory: everything the SM has beyond the kernel's static allocation
+            cudaFuncAttributes fa;
+            ce = cudaFuncGetAttributes(&fa, k_qmlp2<S, ACT, NL, true, true>);
+            if (ce != cudaSuccess) return ce;
+            const_cast<azg_engine*>(e)->tsm_smem_max = e->smem_optin - std::min(e->smem_optin, fa.sharedSizeBytes);
+            ce = cudaFuncSetAttribute(k_qmlp2<S, ACT, NL, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tsm_smem_max);
+            if (ce != cudaSuccess) return ce;
+        }
         // search_wg.cuh raises its 16 tree + evaluation warps to 104 registers with setmaxnreg: the CTA's pool (640 threads x the
         // kernel's register count) must hold 512 x 104 + 128 x 56, or the instruction would wait forever
         cudaFuncAttributes fa;
@@ -584,7 +595,21 @@ static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const
         // in the two-phase kernel 16 warps share a tile and a thin batch finishes a simulation in ~24 us.  From about three full
         // tiles per SM on, the independent warpgroups win (the tree step of one hides under the evaluation of the others).
         const bool two_phase = e->fused_mode == 1 || (e->fused_mode == 0 && (hi - lo) < 3 * 128 * e->sm_count);
-        if (two_phase) {
+        // Discrete search, thin batch: when the rows of ceil(trees / SMs) trees fit in an SM's shared memory next to the evaluation's
+        // operands, the CTA keeps its trees there for the whole search (tree_discrete.cuh ds_step; BASELINE config 3: 28 trees per SM)
+        int tsm_per = 0;
+        if constexpr (S == 4) {
+            const int per = (hi - lo + e->sm_count - 1) / e->sm_count;
+            if (two_phase && !p.rng_mt && !getenv("AZG_NO_TSM") && per <= 128 &&
+                qmlp2_tsm_smem_bytes(NL, e->qfl_count, per, p.R) <= e->tsm_smem_max)
+                tsm_per = per;
+        }
+        if (tsm_per) {
+            if constexpr (S == 4) {
+                const int grid = (hi - lo + tsm_per - 1) / tsm_per;
+                ce = launch_ex(e, k_qmlp2<S, ACT, NL, true, true>, grid, Q2_THREADS, qmlp2_tsm_smem_bytes(NL, e->qfl_count, tsm_per, p.R), st, m, p, N, lo, hi);
+            }
+        } else if (two_phase) {
             const int grid = std::max(1, std::min((hi - lo + 127) / 128, e->sm_count));
             ce = launch_ex(e, k_qmlp2<S, ACT, NL, true>, grid, Q2_THREADS, e->qmlp_smem, st, m, p, N, lo, hi);
         } else {

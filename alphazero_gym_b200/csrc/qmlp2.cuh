@@ -40,6 +40,12 @@
 __host__ __device__ inline size_t qmlp2_smem_bytes(int NL, int qfl_count, bool fused = false) {
     return (size_t)NL * 3 * QMLP_PLANE + 2 * 3 * QMLP_PLANE + (size_t)qfl_count * 4 + 2 * 4 * 128 * 4 + 1024 + (fused ? Q2_TAB_BYTES : 0);
 }
+// TSM (trees in shared memory, tree_discrete.cuh ds_step): one tile per CTA, so ONE A-operand slot; behind the tables the rows,
+// per-tree scalars, network inputs and leaf words of the CTA's trees
+#define Q2_TSM_PER_TREE(R) ((size_t)(R) * (sizeof(DRow) + 2) + sizeof(STree) + sizeof(float4) + sizeof(int32_t))
+__host__ __device__ inline size_t qmlp2_tsm_smem_bytes(int NL, int qfl_count, int trees, int R) {
+    return qmlp2_smem_bytes(NL, qfl_count, true) - 3 * QMLP_PLANE + 64 + (size_t)trees * Q2_TSM_PER_TREE(R);
+}
 // row of the digit planes that holds output j: half h = (j/16)%2, D column of the half = 16*(j/32) + j%16
 __host__ __device__ inline int qmlp_perm_row(int j) { return 64 * ((j >> 4) & 1) + 16 * (j >> 5) + (j & 15); }
 
@@ -233,9 +239,11 @@ __device__ __forceinline__ void q2_finish_tile(const MlpParams& p, uint32_t tb, 
 //   instead of arriving in one burst.  The first version (git history, profiles/README.md r1f) overlapped the two phases INSIDE
 //   an SM with two dedicated tree warpgroups; at 48 registers per tree thread and with both code paths fighting for the
 //   instruction cache it reached 80 us per simulation against 74 us for separate launches.
-template <int S, int ACT, int NL, bool FUSED>
+// TSM (FUSED, discrete tree, thin batches): the CTA's trees live in shared memory for the whole search (tree_discrete.cuh ds_step).
+template <int S, int ACT, int NL, bool FUSED, bool TSM = false>
 __global__ void __launch_bounds__(Q2_THREADS, 1)
-k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chunk_begin, const int chunk_end) {
+k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int chunk_begin, const int chunk_end) {
+    static_assert(!TSM || (FUSED && S == 4), "trees in shared memory: whole-search kernel of the discrete tree");
     extern __shared__ __align__(1024) uint8_t qsm_raw[];
     __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2], hfull[2], hfree[2], phase_bar;
     __shared__ uint32_t tmem_base_s;
@@ -244,8 +252,8 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
     uint8_t* qsm = qsm_raw + ((1024u - (smem_u32(qsm_raw) & 1023u)) & 1023u);
     int8_t* sB = reinterpret_cast<int8_t*>(qsm);                     // [NL][3][8][128][16], rows permuted
     int8_t* sA = sB + (size_t)NL * 3 * QMLP_PLANE;                   // [2][3][8][128][16]
-    float* fl = reinterpret_cast<float*>(sA + 2 * 3 * QMLP_PLANE);   // W0t[S][H], b0[H], NL x (cw, bias)[H], Wh[H][PO_PAD], bh[PO_PAD]
-    float* pmax = fl + p.qfl_count;                                  // [2][4][128]
+    float* fl = reinterpret_cast<float*>(sA + (TSM ? 1 : 2) * 3 * QMLP_PLANE);   // W0t[S][H], b0[H], NL x (cw, bias)[H], Wh[H][PO_PAD], bh[PO_PAD]
+    float* pmax = fl + p_in.qfl_count;                               // [2][4][128]
     double* s_rcp = reinterpret_cast<double*>(pmax + 2 * 4 * 128);   // whole-search kernel: [FUSED_TAB + 1] each
     double* s_sq = s_rcp + FUSED_TAB + 1;
     int32_t* s_pw = reinterpret_cast<int32_t*>(s_sq + FUSED_TAB + 1);
@@ -253,7 +261,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // this CTA's contiguous row range, cut into an even number of equal tiles of at most 128 rows
-    const int first = FUSED ? chunk_begin : 0, last = FUSED ? chunk_end : p.n;
+    const int first = FUSED ? chunk_begin : 0, last = FUSED ? chunk_end : p_in.n;
     const int per = (last - first + gridDim.x - 1) / gridDim.x;
     const int row_begin = first + blockIdx.x * per;
     const int row_end = min(row_begin + per, last);
@@ -262,6 +270,26 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
     const int nrows = row_end - row_begin;
     int ntiles = (nrows + 127) / 128;
     if (ntiles > 1) ntiles = (ntiles + 1) & ~1;
+    // TSM: shared-memory tables of the CTA's trees behind the lookup tables; the evaluation reads its inputs (X, leaf words) from and
+    // writes V / priors into them through a patched copy of the parameter block (generic addresses that point into shared memory)
+    SmTrees smt;
+    {
+        uint8_t* tbase = reinterpret_cast<uint8_t*>(s_pw + FUSED_TAB + 1);
+        tbase += (64u - (smem_u32(tbase) & 63u)) & 63u;
+        smt.rows = reinterpret_cast<DRow*>(tbase);
+        smt.st = reinterpret_cast<STree*>(smt.rows + (size_t)(TSM ? nrows : 0) * tp.R);
+        smt.X = reinterpret_cast<float4*>(smt.st + (TSM ? nrows : 0));
+        smt.leaf = reinterpret_cast<int32_t*>(smt.X + (TSM ? nrows : 0));
+        smt.path = reinterpret_cast<uint16_t*>(smt.leaf + (TSM ? nrows : 0));
+    }
+    MlpParams p_tsm;
+    if (TSM) {
+        p_tsm = p_in;
+        p_tsm.X = reinterpret_cast<const float*>(smt.X) - (ptrdiff_t)row_begin * 4;
+        p_tsm.leaf = smt.leaf - row_begin;
+        p_tsm.drows = smt.rows - (ptrdiff_t)row_begin * tp.R;
+    }
+    const MlpParams& p = TSM ? p_tsm : p_in;
     // full tiles first, the remainder in the last one(s): epilogue work is spent per 32-row group, so 443 rows cost 14 row groups
     // as 128 + 128 + 128 + 59 against 16 as four tiles of 111 (the warps of the empty row groups leave their issue slots to the others)
     const int th = 128;
@@ -402,7 +430,8 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
         uint32_t pph = 0;  // parity of the next phase boundary
         if (FUSED) {  // MCTSContinuous.initialize_search for every tree of the CTA
             for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
-                if (S == 4) d_init(tp, row_begin + i);  // state_dim 4 = CartPole = the discrete tree (engine.cu checks it)
+                if (TSM) ds_init(tp, smt, i, row_begin + i);
+                else if (S == 4) d_init(tp, row_begin + i);  // state_dim 4 = CartPole = the discrete tree (engine.cu checks it)
                 else c_init(tp, row_begin + i);
             }
             phase_sync(&phase_bar, pph);
@@ -502,6 +531,12 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
             const long long c0 = clock64();
             phase_sync(&phase_bar, pph);  // the post-processing warps have finished every row of this evaluation
             const long long c1 = clock64();
+            if (TSM) {
+                // a group of lpt consecutive lanes per tree (tree_discrete.cuh ds_step): 28 trees = 28 half warps on 14 warps
+                const int lpt = nrows <= 16 ? 32 : (nrows <= 32 ? 16 : (nrows <= 64 ? 8 : 4));
+                const int i = tid / lpt;
+                if ((tid & ~31) / lpt < nrows) ds_step(tp, tabs, smt, i, row_begin + i, i < nrows, lane, lpt, s > 0, s + 1 < n_evals);
+            } else
 #pragma unroll 1
             for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
                 const int gr = row_begin + i;
@@ -517,6 +552,7 @@ k_qmlp2(const MlpParams p, const TreeParams tp, const int n_sims, const int chun
             cyc_tree += clock64() - c1;
         }
         }
+        if (TSM) ds_writeback(tp, smt, nrows, row_begin, tid, Q2_EPI_THREADS);  // after the last phase boundary: the rows are final
         if (FUSED && tid == 0 && p.stats) {
             atomicAdd(p.stats + 0, (unsigned long long)(clock64() - cyc_begin));
             atomicAdd(p.stats + 1, (unsigned long long)cyc_tree);

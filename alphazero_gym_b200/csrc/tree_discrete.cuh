@@ -237,6 +237,286 @@ __global__ void __launch_bounds__(128) k_step_discrete(const TreeParams p) {
     if (t < p.B) d_step(p, tb, t, BACKUP, SELECT);
 }
 
+// ---- shared-memory-resident trees (whole-search kernel, thin batches: qmlp2.cuh TSM) -----------------------------------------------
+// At BASELINE config 3 (4096 CartPole trees x 50 simulations) a B200 holds 28 trees per SM, and their rows -- 28 x 52 x 64 B = 93 KB --
+// fit next to the evaluation's operands in the SM's 227 KB of shared memory.  The tree step is a chain of dependent row visits
+// (CartPole traces are ~10 levels deep) and with the rows in HBM / L2 every visit is a ~700-cycle round trip executed by a lone
+// warp: 25 us of a 32 us simulation (profiles/README.md r2e).  From shared memory a visit is ~30 cycles, the backup can simply follow
+// the parent links again (mcts.py:241-267 as written) and needs no recorded path, and the per-tree scalars never leave the SM.
+// Same arithmetic in the same order as d_step: results are bit-identical.  The rows are copied to p.drows when the search ends
+// (k_results_discrete, azg_dump_tree, the self-play step and tree reuse read them there); the env states stay in p.dstate.
+struct __align__(16) STree {  // per-tree scalars (p.leaf / p.n_rows / p.draws / p.ctr / p.ddepth of the global-memory path)
+    int32_t n_rows, draws;
+    uint32_t levels;        // levels descended, summed over the search
+    uint16_t terms, depth;  // simulations that ended on an existing terminal node; length of the current simulation's path
+};
+struct SmTrees {
+    DRow* rows;      // [trees][R]
+    STree* st;       // [trees]
+    float4* X;       // [trees]  network input of the leaf
+    int32_t* leaf;   // [trees]  LEAF_* word
+    uint16_t* path;  // [trees][R]  recorded path of the current simulation
+};
+
+// a / b for a small integer b through the reciprocal table, without the range checks of div_small (the caller has made them)
+__device__ __forceinline__ double div_tab(double a, int b, const double* rcp) {
+    const double y = rcp[b];
+    const double q = __dmul_rn(a, y);
+    const double r = __fma_rn(-q, (double)b, a);
+    return __fma_rn(r, y, q);
+}
+// numerators for which div_tab is the correctly rounded quotient: normal numbers well inside the exponent range (a strict subset of
+// div_small's 1e-250 < |a| < 1e250; zero, tiny and non-finite values take the checked form)
+__device__ __forceinline__ bool div_tab_ok(double a) {
+    const uint32_t e = ((uint32_t)__double2hiint(a) >> 20) & 0x7ffu;
+    return (e - 0xC2u) < 0x67Bu;
+}
+
+__device__ __forceinline__ void ds_init(const TreeParams& p, const SmTrees& sm, int i, int t) {
+    const double* s = p.root_state + (size_t)t * 4;
+    double* st = p.dstate + (size_t)t * p.R * 4;
+    DRow row;
+    row.W[0] = row.W[1] = 0.0;
+    row.r = 0.0;
+    row.n_e[0] = row.n_e[1] = 0;
+    row.prior[0] = row.prior[1] = 0.0f;
+    row.V = 0.0f;
+    row.node_n = p.root_n_init ? p.root_n_init[t] : 0;
+    row.child[0] = row.child[1] = DROW_NONE;
+    row.parent = DROW_NONE;
+    row.paction = 0;
+    row.flags = 0;
+    row.pad[0] = row.pad[1] = 0;
+    sm.rows[(size_t)i * p.R] = row;
+    st[0] = s[0]; st[1] = s[1]; st[2] = s[2]; st[3] = s[3];
+    sm.X[i] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
+    sm.leaf[i] = 0 | LEAF_EVAL;
+    STree z;
+    z.n_rows = 1; z.draws = 0; z.levels = 0; z.terms = 0; z.depth = 0;
+    sm.st[i] = z;
+    p.ctr[(size_t)3 * p.B + t] = 0;  // evaluation counter (the post-processing warps add to it when the search ends)
+}
+
+// Philox4x32-10 block of one selection draw (stream 0, block 0; rng_block), word .x, fully unrolled
+__device__ __forceinline__ uint32_t philox_draw_x(uint32_t k0, uint32_t k1, uint32_t tree_lo, uint32_t tree_hi, uint32_t idx) {
+    uint32_t cx = idx, cy = 0u, cz = tree_lo, cw = tree_hi;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, cx), lo0 = 0xD2511F53u * cx;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, cz), lo1 = 0xCD9E8D57u * cz;
+        cx = hi1 ^ cy ^ k0;
+        cy = lo1;
+        cz = hi0 ^ cw ^ k1;
+        cw = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return cx;
+}
+
+// The selection rule of one node as a function of its statistics (mcts.py:483-484 + helpers.argmax): bit 0 = arg max of the two PUCT
+// scores, bit 1 = the scores are equal (random tie-break), bit 2 = a score is NaN.  Straight-line code: one combined guard in front
+// of four reciprocal-table divisions (Markstein); large counts and unusual numerators take the checked forms.
+#define DS_DEC_A 1u
+#define DS_DEC_TIE 2u
+#define DS_DEC_NAN 4u
+__device__ __forceinline__ uint32_t ds_decide(const TreeParams& p, const Tabs& tb, double W0, double W1, int n0, int n1, float pr0, float pr1,
+                                              float V, int nn) {  // nn = node.n + 1
+    const float cuf = (float)p.c_uct;
+    const double pc0 = p.puct_f32 ? (double)__fmul_rn(pr0, cuf) : (double)pr0 * p.c_uct;
+    const double pc1 = p.puct_f32 ? (double)__fmul_rn(pr1, cuf) : (double)pr1 * p.c_uct;
+    double u0, u1;
+    if (nn <= tb.n && n0 < tb.n && n1 < tb.n && (n0 == 0 || div_tab_ok(W0)) && (n1 == 0 || div_tab_ok(W1))) {
+        const double sq = tb.sq[nn];
+        const double q0 = div_tab(W0, n0 > 0 ? n0 : 1, tb.rcp), q1 = div_tab(W1, n1 > 0 ? n1 : 1, tb.rcp);
+        const double e0 = div_tab(sq, n0 + 1, tb.rcp), e1 = div_tab(sq, n1 + 1, tb.rcp);
+        u0 = (n0 > 0 ? q0 : (double)V) + pc0 * e0;
+        u1 = (n1 > 0 ? q1 : (double)V) + pc1 * e1;
+    } else {
+        const double sq = sqrt_small(nn, tb.sq, tb.n);
+        u0 = (n0 > 0 ? div_small(W0, n0, tb.rcp, tb.n) : (double)V) + pc0 * div_small(sq, n0 + 1, tb.rcp, tb.n);
+        u1 = (n1 > 0 ? div_small(W1, n1, tb.rcp, tb.n) : (double)V) + pc1 * div_small(sq, n1 + 1, tb.rcp, tb.n);
+    }
+    return (u1 > u0 ? DS_DEC_A : 0u) | (u0 == u1 ? DS_DEC_TIE : 0u) | ((u0 != u0 || u1 != u1) ? DS_DEC_NAN : 0u);
+}
+
+// One simulation step of the trees of a WARP on the shared-memory tables: a group of `lpt` consecutive lanes (4 .. 32, a power of two)
+// per tree; all 32 lanes call this together (`valid`: this lane's group has a tree, i = its index in the CTA, t = its global id).
+//
+// ncu on the one-thread-per-tree version (profiles/README.md r2g): ~3200 warp instructions per tree step, issued at ~9 cycles each
+// by warps with two active lanes -- the step is bound by the LENGTH of its dependent instruction stream.  This version shortens it:
+//   * a node's selection rule (ds_decide) only changes when a backup passes through the node, so it is evaluated THERE, for all
+//     levels of the path at once (lane j owns level j), and cached in the row (DRow::pad[0]); the descent reads one 16-byte piece
+//     per level (children + cached rule) -- about ten instructions;
+//   * the return R = r + gamma R is the only sequential part of the backup: it runs down the levels in registers (the r values come
+//     by shuffle), the statistics of all levels are updated in parallel;
+//   * the selection draws of the next lpt indices are generated at once, one Philox block per lane, and reduced with two ballots
+//     to bit masks (epsilon test / random action per level) -- the generator was 1200 of the 3200 instructions.
+// Same arithmetic on the same inputs as d_step: results are bit-identical.
+__device__ __forceinline__ void ds_step(const TreeParams& p, const Tabs& tb, const SmTrees& sm, int i, int t, bool valid, int lane, int lpt,
+                                        const bool BACKUP, const bool SELECT) {
+    const uint32_t FULL = 0xFFFFFFFFu;
+    if (!valid) i = 0;  // lanes without a tree read tree 0's tables and write nothing
+    DRow* rows = sm.rows + (size_t)i * p.R;
+    uint16_t* path = sm.path + (size_t)i * p.R;  // (row << 1 | action) per level of the current simulation, root first
+    const int gl = lane & (lpt - 1), gbase = lane - gl;
+    {
+        // R = leaf.V; up the path: R = node.r + gamma*R; edge.n += 1; edge.W += R; parent.n += 1 (mcts.py:241-267); then the selection
+        // rule of every node whose statistics changed, and of the leaf (whose V and priors the evaluation has just written)
+        const int leaf = sm.leaf[i] & LEAF_ROW_MASK;
+        const int d = BACKUP ? (int)sm.st[i].depth : 0;
+        double Rv = (double)rows[leaf].V;
+        int hi = valid ? d + 1 : 0;  // items [0, d]: the levels of the path and the leaf
+#pragma unroll 1
+        while (__any_sync(FULL, hi > 0)) {
+            const int lo = hi > lpt ? hi - lpt : 0;
+            const int j = lo + gl;  // this lane's item
+            const bool act = j < hi, lvl = act && j < d;
+            const int e = lvl ? (int)path[j] : 0;
+            const int cj = lvl ? (j + 1 < d ? (int)(path[j + 1] >> 1) : leaf) : 0;  // the node level j leads to
+            const double rj = rows[cj].r;
+            const int nrow = lvl ? (e >> 1) : leaf;
+            const uint4* rp = reinterpret_cast<const uint4*>(rows + nrow);
+            const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+            const int nlev = __reduce_max_sync(FULL, (hi < d ? hi : d) - lo);  // levels in this chunk, largest over the warp's groups
+            double myR = 0.0;
+#pragma unroll 1
+            for (int sl = nlev - 1; sl >= 0; --sl) {
+                const double rq = __shfl_sync(FULL, rj, gbase + sl);
+                const int q = lo + sl;
+                if (q < hi && q < d) {
+                    Rv = rq + p.gamma * Rv;
+                    if (q == j) myR = Rv;
+                }
+            }
+            if (act) {
+                double W0 = __hiloint2double((int)q0.y, (int)q0.x), W1 = __hiloint2double((int)q0.w, (int)q0.z);
+                int n0 = (int)q1.z, n1 = (int)q1.w, nn = (int)q2.w;
+                DRow* pr = rows + nrow;
+                if (lvl) {  // the nodes of a path are distinct: no two lanes touch the same row
+                    const int pa = e & 1;
+                    if (pa) { W1 += myR; n1 += 1; pr->W[1] = W1; pr->n_e[1] = n1; }
+                    else { W0 += myR; n0 += 1; pr->W[0] = W0; pr->n_e[0] = n0; }
+                    nn += 1;
+                    pr->node_n = nn;
+                }
+                pr->pad[0] = ds_decide(p, tb, W0, W1, n0, n1, __uint_as_float(q2.x), __uint_as_float(q2.y), __uint_as_float(q2.z), nn + 1);
+            }
+            hi = lo;
+        }
+        __syncwarp();
+    }
+    if (SELECT) {
+        const int64_t tree = tree_base(p) + t;
+        const uint64_t seed = __ldg(p.seedp);
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), tlo = (uint32_t)tree, thi = (uint32_t)((uint64_t)tree >> 32);
+        STree st = sm.st[i];
+        const bool eps = p.epsilon != 0;
+        const int dpl = eps ? 2 : 1;       // draws per level: random() of epsilon_greedy (if epsilon != 0), then randint / choice
+        const int lpb = lpt / dpl;         // levels served by one batch of lpt draws
+        uint32_t RP = 0, RB = 0;           // per draw of the batch: random() < epsilon; the random action
+        int cur = 0, a = -1, levels = 0;
+        bool active = valid, expand = false, nan = false;
+        int L = 0;                         // level index, the same for every group of the warp that is still descending
+#pragma unroll 1
+        while (__any_sync(FULL, active)) {
+            const int kb = L % lpb;
+            if (kb == 0) {  // draws st.draws + dpl * L + [0, lpt)
+                const uint32_t x = philox_draw_x(k0, k1, tlo, thi, (uint32_t)(st.draws + dpl * L + gl));
+                const bool lt = (double)u32_to_unit(x) < p.epsilon;
+                RP = __ballot_sync(FULL, lt) >> gbase;
+                RB = __ballot_sync(FULL, u32_to_index(x, 2) != 0) >> gbase;
+            }
+            if (active) {
+                const uint4 q3 = reinterpret_cast<const uint4*>(rows + cur)[3];  // child[0] | child[1] << 16, parent | paction | flags, rule, -
+                if (L > 0 && ((q3.y >> 24) & ROW_TERMINAL)) {  // trace ends on an existing terminal node
+                    a = -1;
+                    active = false;
+                } else {
+                    const bool rpick = eps && ((RP >> (2 * kb)) & 1u);
+                    const int rbit = (int)((RB >> (dpl * kb + dpl - 1)) & 1u);
+                    a = (rpick || (q3.z & DS_DEC_TIE)) ? rbit : (int)(q3.z & DS_DEC_A);
+                    nan |= (q3.z & DS_DEC_NAN) != 0;
+                    if (gl == 0) path[L] = (uint16_t)((cur << 1) | a);
+                    ++levels;
+                    const int child = (int)(a ? (q3.x >> 16) : (q3.x & 0xFFFFu));
+                    if (child == DROW_NONE) { active = false; expand = true; }
+                    else cur = child;
+                }
+            }
+            ++L;
+        }
+        if (valid && gl == 0) {
+            if (nan) atomicOr(p.err, ERR_NAN);
+            st.draws += dpl * levels;
+            st.levels += (uint32_t)levels;
+            st.depth = (uint16_t)levels;
+            if (expand) {
+                const int child = st.n_rows;
+                if (child >= p.R) {
+                    atomicOr(p.err, ERR_CAPACITY);
+                    sm.leaf[i] = cur;
+                    st.depth = 0;
+                } else {
+                    st.n_rows = child + 1;
+                    const double* sp = p.dstate + ((size_t)t * p.R + cur) * 4;
+                    const double s[4] = {sp[0], sp[1], sp[2], sp[3]};
+                    double o[4], rew;
+                    const bool term = env::cartpole_step(s, a, o, rew);
+                    double* so = p.dstate + ((size_t)t * p.R + child) * 4;
+                    so[0] = o[0]; so[1] = o[1]; so[2] = o[2]; so[3] = o[3];
+                    DRow nr;
+                    nr.W[0] = nr.W[1] = 0.0;
+                    nr.r = rew;
+                    nr.n_e[0] = nr.n_e[1] = 0;
+                    nr.prior[0] = nr.prior[1] = 0.0f;
+                    nr.V = 0.0f;
+                    nr.node_n = 0;
+                    nr.child[0] = nr.child[1] = DROW_NONE;
+                    nr.parent = (uint16_t)cur;
+                    nr.paction = (uint8_t)a;
+                    nr.flags = term ? ROW_TERMINAL : 0;
+                    nr.pad[0] = nr.pad[1] = 0;
+                    rows[child] = nr;
+                    rows[cur].child[a] = (uint16_t)child;
+                    sm.X[i] = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+                    sm.leaf[i] = child | LEAF_EVAL | (term ? LEAF_TERMINAL : 0);
+                }
+            } else {
+                sm.leaf[i] = cur;
+                st.terms += 1;
+            }
+            sm.st[i] = st;
+        }
+        __syncwarp();
+    }
+}
+
+// end of the search: rows in use and per-tree scalars back to the global tables (cooperatively, `nthreads` threads of the CTA)
+__device__ __forceinline__ void ds_writeback(const TreeParams& p, const SmTrees& sm, int ntrees, int t0, int tid, int nthreads) {
+    const int per_tree = p.R * 4;  // 16-byte pieces per tree
+    const uint4* src = reinterpret_cast<const uint4*>(sm.rows);
+    uint4* dst = reinterpret_cast<uint4*>(p.drows + (size_t)t0 * p.R);
+    for (int k = tid; k < ntrees * per_tree; k += nthreads) {
+        const int i = k / per_tree, off = k - i * per_tree;
+        if (off < sm.st[i].n_rows * 4) {
+            uint4 v = src[k];
+            if ((off & 3) == 3) v.z = 0u;  // DRow::pad[0] held the cached selection rule
+            dst[k] = v;
+        }
+    }
+    for (int i = tid; i < ntrees; i += nthreads) {
+        const STree st = sm.st[i];
+        const int t = t0 + i;
+        p.n_rows[t] = st.n_rows;
+        p.draws[t] = st.draws;
+        p.leaf[t] = sm.leaf[i];
+        p.ctr[t] = st.levels;
+        p.ctr[(size_t)p.B + t] = st.levels * 2;
+        p.ctr[(size_t)2 * p.B + t] = st.terms;
+    }
+}
+
 // MCTS.return_results (mcts.py:269-307) for the discrete root
 __global__ void k_results_discrete(const TreeParams p, int cmax, float* actions, int32_t* counts, double* Q, double* Vt,
                                    int32_t* nchild) {
