@@ -247,6 +247,8 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
     extern __shared__ __align__(1024) uint8_t qsm_raw[];
     __shared__ __align__(8) uint64_t wbar, full[2], ready[2], freeb[2], hfull[2], hfree[2], phase_bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ DsCtx s_dsctx;  // TSM: context of the tree phase (tree_discrete.cuh ds_phase)
+    __shared__ unsigned long long s_dsprof[8];
     // round up to 1024 B with an OFFSET on the shared pointer: a round trip through uintptr_t loses the address space and every
     // access below becomes a generic LD/ST (long-scoreboard latency) instead of LDS/STS
     uint8_t* qsm = qsm_raw + ((1024u - (smem_u32(qsm_raw) & 1023u)) & 1023u);
@@ -290,6 +292,23 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
         p_tsm.drows = smt.rows - (ptrdiff_t)row_begin * tp.R;
     }
     const MlpParams& p = TSM ? p_tsm : p_in;
+    if (TSM && tid == 0) {
+        DsCtx cx;
+        cx.sm = smt;
+        cx.dstate = tp.dstate + (size_t)row_begin * tp.R * 4;
+        cx.err = tp.err;
+        cx.rcp = s_rcp; cx.sq = s_sq;
+        cx.gamma = tp.gamma; cx.epsilon = tp.epsilon; cx.c_uct = tp.c_uct;
+        const uint64_t seed = __ldg(tp.seedp);
+        cx.k0 = (uint32_t)seed; cx.k1 = (uint32_t)(seed >> 32);
+        cx.tree0 = tree_base(tp) + row_begin;
+        cx.tabn = FUSED_TAB; cx.R = tp.R; cx.puct_f32 = tp.puct_f32; cx.ntrees = nrows;
+        cx.lpt = nrows <= 16 ? 32 : (nrows <= 32 ? 16 : (nrows <= 64 ? 8 : 4));  // a group of lpt consecutive lanes per tree: 28 trees = 28 half warps
+        cx.pad = 0;
+        cx.prof = s_dsprof;
+        for (int k = 0; k < 8; ++k) s_dsprof[k] = 0;
+        s_dsctx = cx;
+    }
     // full tiles first, the remainder in the last one(s): epilogue work is spent per 32-row group, so 443 rows cost 14 row groups
     // as 128 + 128 + 128 + 59 against 16 as four tiles of 111 (the warps of the empty row groups leave their issue slots to the others)
     const int th = 128;
@@ -532,10 +551,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
             phase_sync(&phase_bar, pph);  // the post-processing warps have finished every row of this evaluation
             const long long c1 = clock64();
             if (TSM) {
-                // a group of lpt consecutive lanes per tree (tree_discrete.cuh ds_step): 28 trees = 28 half warps on 14 warps
-                const int lpt = nrows <= 16 ? 32 : (nrows <= 32 ? 16 : (nrows <= 64 ? 8 : 4));
-                const int i = tid / lpt;
-                if ((tid & ~31) / lpt < nrows) ds_step(tp, tabs, smt, i, row_begin + i, i < nrows, lane, lpt, s > 0, s + 1 < n_evals);
+                ds_phase(&s_dsctx, (s > 0 ? 1 : 0) | (s + 1 < n_evals ? 2 : 0));
             } else
 #pragma unroll 1
             for (int i = tid; i < nrows; i += Q2_EPI_THREADS) {
@@ -558,6 +574,9 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
             atomicAdd(p.stats + 1, (unsigned long long)cyc_tree);
             atomicAdd(p.stats + 2, (unsigned long long)cyc_sync);
             atomicAdd(p.stats + 4, 1ull);
+#ifdef AZG_TREE_PROF
+            if (TSM) for (int k = 0; k < 8; ++k) atomicAdd(p.stats + 8 + k, s_dsprof[k]);
+#endif
         }
     }
     tc_fence_before();

@@ -257,6 +257,21 @@ struct SmTrees {
     int32_t* leaf;   // [trees]  LEAF_* word
     uint16_t* path;  // [trees][R]  recorded path of the current simulation
 };
+// Everything the tree phase needs, written once per launch into shared memory by the kernel and copied into registers when the
+// phase starts: with the kernel's own parameter blocks (and ~70 registers of the epilogue live across the phase) the compiler
+// rematerialised every address inside the level loop -- 75 instructions per level (profiles/README.md r2i)
+struct __align__(16) DsCtx {
+    SmTrees sm;
+    double* dstate;      // env states of the CTA's tree 0 (global memory)
+    int32_t* err;
+    const double* rcp;   // lookup tables (shared memory): 1 / i, sqrt(i), i <= tabn
+    const double* sq;
+    double gamma, epsilon, c_uct;
+    uint32_t k0, k1;     // Philox key
+    int64_t tree0;       // global id of the CTA's tree 0
+    int32_t tabn, R, puct_f32, ntrees, lpt, pad;
+    unsigned long long* prof;  // AZG_TREE_PROF builds: per-section cycles of warp 0 (shared memory, no atomics)
+};
 
 // a / b for a small integer b through the reciprocal table, without the range checks of div_small (the caller has made them)
 __device__ __forceinline__ double div_tab(double a, int b, const double* rcp) {
@@ -320,22 +335,22 @@ __device__ __forceinline__ uint32_t philox_draw_x(uint32_t k0, uint32_t k1, uint
 #define DS_DEC_A 1u
 #define DS_DEC_TIE 2u
 #define DS_DEC_NAN 4u
-__device__ __forceinline__ uint32_t ds_decide(const TreeParams& p, const Tabs& tb, double W0, double W1, int n0, int n1, float pr0, float pr1,
-                                              float V, int nn) {  // nn = node.n + 1
-    const float cuf = (float)p.c_uct;
-    const double pc0 = p.puct_f32 ? (double)__fmul_rn(pr0, cuf) : (double)pr0 * p.c_uct;
-    const double pc1 = p.puct_f32 ? (double)__fmul_rn(pr1, cuf) : (double)pr1 * p.c_uct;
+__device__ __forceinline__ uint32_t ds_decide(const DsCtx& cx, double W0, double W1, int n0, int n1, float pr0, float pr1, float V,
+                                              int nn) {  // nn = node.n + 1
+    const float cuf = (float)cx.c_uct;
+    const double pc0 = cx.puct_f32 ? (double)__fmul_rn(pr0, cuf) : (double)pr0 * cx.c_uct;
+    const double pc1 = cx.puct_f32 ? (double)__fmul_rn(pr1, cuf) : (double)pr1 * cx.c_uct;
     double u0, u1;
-    if (nn <= tb.n && n0 < tb.n && n1 < tb.n && (n0 == 0 || div_tab_ok(W0)) && (n1 == 0 || div_tab_ok(W1))) {
-        const double sq = tb.sq[nn];
-        const double q0 = div_tab(W0, n0 > 0 ? n0 : 1, tb.rcp), q1 = div_tab(W1, n1 > 0 ? n1 : 1, tb.rcp);
-        const double e0 = div_tab(sq, n0 + 1, tb.rcp), e1 = div_tab(sq, n1 + 1, tb.rcp);
+    if (nn <= cx.tabn && n0 < cx.tabn && n1 < cx.tabn && (n0 == 0 || div_tab_ok(W0)) && (n1 == 0 || div_tab_ok(W1))) {
+        const double sq = cx.sq[nn];
+        const double q0 = div_tab(W0, n0 > 0 ? n0 : 1, cx.rcp), q1 = div_tab(W1, n1 > 0 ? n1 : 1, cx.rcp);
+        const double e0 = div_tab(sq, n0 + 1, cx.rcp), e1 = div_tab(sq, n1 + 1, cx.rcp);
         u0 = (n0 > 0 ? q0 : (double)V) + pc0 * e0;
         u1 = (n1 > 0 ? q1 : (double)V) + pc1 * e1;
     } else {
-        const double sq = sqrt_small(nn, tb.sq, tb.n);
-        u0 = (n0 > 0 ? div_small(W0, n0, tb.rcp, tb.n) : (double)V) + pc0 * div_small(sq, n0 + 1, tb.rcp, tb.n);
-        u1 = (n1 > 0 ? div_small(W1, n1, tb.rcp, tb.n) : (double)V) + pc1 * div_small(sq, n1 + 1, tb.rcp, tb.n);
+        const double sq = sqrt_small(nn, cx.sq, cx.tabn);
+        u0 = (n0 > 0 ? div_small(W0, n0, cx.rcp, cx.tabn) : (double)V) + pc0 * div_small(sq, n0 + 1, cx.rcp, cx.tabn);
+        u1 = (n1 > 0 ? div_small(W1, n1, cx.rcp, cx.tabn) : (double)V) + pc1 * div_small(sq, n1 + 1, cx.rcp, cx.tabn);
     }
     return (u1 > u0 ? DS_DEC_A : 0u) | (u0 == u1 ? DS_DEC_TIE : 0u) | ((u0 != u0 || u1 != u1) ? DS_DEC_NAN : 0u);
 }
@@ -353,117 +368,167 @@ __device__ __forceinline__ uint32_t ds_decide(const TreeParams& p, const Tabs& t
 //   * the selection draws of the next lpt indices are generated at once, one Philox block per lane, and reduced with two ballots
 //     to bit masks (epsilon test / random action per level) -- the generator was 1200 of the 3200 instructions.
 // Same arithmetic on the same inputs as d_step: results are bit-identical.
-__device__ __forceinline__ void ds_step(const TreeParams& p, const Tabs& tb, const SmTrees& sm, int i, int t, bool valid, int lane, int lpt,
-                                        const bool BACKUP, const bool SELECT) {
+#ifdef AZG_TREE_PROF
+#define DSP_BEGIN() long long dsp_last = clock64()
+#define DSP_STAMP(k) do { const long long _t = clock64(); if (threadIdx.x == 0) cx.prof[k] += (unsigned long long)(_t - dsp_last); dsp_last = _t; } while (0)
+#else
+#define DSP_BEGIN()
+#define DSP_STAMP(k)
+#endif
+// shared-memory accesses by 32-bit address: the tables' pointers come out of DsCtx, so the compiler cannot know their address space
+__device__ __forceinline__ uint4 ds_lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ds_lds64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ds_lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ds_lds16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ds_sts64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void ds_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void ds_sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+
+__device__ __forceinline__ void ds_step(const DsCtx& cx, int i, bool valid, int lane, const bool BACKUP, const bool SELECT) {
     const uint32_t FULL = 0xFFFFFFFFu;
+    DSP_BEGIN();
     if (!valid) i = 0;  // lanes without a tree read tree 0's tables and write nothing
-    DRow* rows = sm.rows + (size_t)i * p.R;
-    uint16_t* path = sm.path + (size_t)i * p.R;  // (row << 1 | action) per level of the current simulation, root first
+    const SmTrees sm = cx.sm;
+    const int lpt = cx.lpt, R = cx.R;
+    DRow* rows = sm.rows + (size_t)i * R;
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);                          // row k of this tree at rows_s + 64 k
+    const uint32_t path_s = (uint32_t)__cvta_generic_to_shared(sm.path + (size_t)i * R);       // (row << 1 | action) of level k at path_s + 2 k
     const int gl = lane & (lpt - 1), gbase = lane - gl;
     {
         // R = leaf.V; up the path: R = node.r + gamma*R; edge.n += 1; edge.W += R; parent.n += 1 (mcts.py:241-267); then the selection
         // rule of every node whose statistics changed, and of the leaf (whose V and priors the evaluation has just written)
         const int leaf = sm.leaf[i] & LEAF_ROW_MASK;
         const int d = BACKUP ? (int)sm.st[i].depth : 0;
-        double Rv = (double)rows[leaf].V;
+        double Rv = (double)__uint_as_float(ds_lds32(rows_s + 64u * leaf + 40u));
+        const double gamma = cx.gamma;
         int hi = valid ? d + 1 : 0;  // items [0, d]: the levels of the path and the leaf
 #pragma unroll 1
         while (__any_sync(FULL, hi > 0)) {
             const int lo = hi > lpt ? hi - lpt : 0;
             const int j = lo + gl;  // this lane's item
             const bool act = j < hi, lvl = act && j < d;
-            const int e = lvl ? (int)path[j] : 0;
-            const int cj = lvl ? (j + 1 < d ? (int)(path[j + 1] >> 1) : leaf) : 0;  // the node level j leads to
-            const double rj = rows[cj].r;
-            const int nrow = lvl ? (e >> 1) : leaf;
-            const uint4* rp = reinterpret_cast<const uint4*>(rows + nrow);
-            const uint4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
-            const int nlev = __reduce_max_sync(FULL, (hi < d ? hi : d) - lo);  // levels in this chunk, largest over the warp's groups
+            const int e = lvl ? (int)ds_lds16(path_s + 2u * j) : 0;
+            const int cj = lvl ? (j + 1 < d ? (int)(ds_lds16(path_s + 2u * j + 2u) >> 1) : leaf) : 0;  // the node level j leads to
+            const double rj = ds_lds64(rows_s + 64u * cj + 16u);
+            const uint32_t nrow_s = rows_s + 64u * (lvl ? (e >> 1) : leaf);
+            const uint4 q0 = ds_lds128(nrow_s), q1 = ds_lds128(nrow_s + 16u), q2 = ds_lds128(nrow_s + 32u);
+            const int top = (hi < d ? hi : d) - lo;                  // levels of the path in this chunk
+            const int nlev = __reduce_max_sync(FULL, top);           // largest over the warp's groups
             double myR = 0.0;
 #pragma unroll 1
             for (int sl = nlev - 1; sl >= 0; --sl) {
                 const double rq = __shfl_sync(FULL, rj, gbase + sl);
-                const int q = lo + sl;
-                if (q < hi && q < d) {
-                    Rv = rq + p.gamma * Rv;
-                    if (q == j) myR = Rv;
+                if (sl < top) {
+                    Rv = rq + gamma * Rv;
+                    if (sl == gl) myR = Rv;
                 }
             }
             if (act) {
                 double W0 = __hiloint2double((int)q0.y, (int)q0.x), W1 = __hiloint2double((int)q0.w, (int)q0.z);
                 int n0 = (int)q1.z, n1 = (int)q1.w, nn = (int)q2.w;
-                DRow* pr = rows + nrow;
                 if (lvl) {  // the nodes of a path are distinct: no two lanes touch the same row
-                    const int pa = e & 1;
-                    if (pa) { W1 += myR; n1 += 1; pr->W[1] = W1; pr->n_e[1] = n1; }
-                    else { W0 += myR; n0 += 1; pr->W[0] = W0; pr->n_e[0] = n0; }
+                    if (e & 1) { W1 += myR; n1 += 1; ds_sts64(nrow_s + 8u, W1); ds_sts32(nrow_s + 28u, (uint32_t)n1); }
+                    else { W0 += myR; n0 += 1; ds_sts64(nrow_s, W0); ds_sts32(nrow_s + 24u, (uint32_t)n0); }
                     nn += 1;
-                    pr->node_n = nn;
+                    ds_sts32(nrow_s + 44u, (uint32_t)nn);
                 }
-                pr->pad[0] = ds_decide(p, tb, W0, W1, n0, n1, __uint_as_float(q2.x), __uint_as_float(q2.y), __uint_as_float(q2.z), nn + 1);
+                ds_sts32(nrow_s + 56u, ds_decide(cx, W0, W1, n0, n1, __uint_as_float(q2.x), __uint_as_float(q2.y), __uint_as_float(q2.z), nn + 1));
             }
             hi = lo;
         }
         __syncwarp();
     }
+    DSP_STAMP(1);
     if (SELECT) {
-        const int64_t tree = tree_base(p) + t;
-        const uint64_t seed = __ldg(p.seedp);
-        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32), tlo = (uint32_t)tree, thi = (uint32_t)((uint64_t)tree >> 32);
+        const int64_t tree = cx.tree0 + i;
+        const uint32_t k0 = cx.k0, k1 = cx.k1, tlo = (uint32_t)tree, thi = (uint32_t)((uint64_t)tree >> 32);
+        const double epsilon = cx.epsilon;
         STree st = sm.st[i];
-        const bool eps = p.epsilon != 0;
-        const int dpl = eps ? 2 : 1;       // draws per level: random() of epsilon_greedy (if epsilon != 0), then randint / choice
-        const int lpb = lpt / dpl;         // levels served by one batch of lpt draws
-        uint32_t RP = 0, RB = 0;           // per draw of the batch: random() < epsilon; the random action
+        const bool eps = epsilon != 0;
+        const int dsh = eps ? 1 : 0;             // draws per level = 1 << dsh: random() of epsilon_greedy (if epsilon != 0), then randint / choice
+        const int nb = lpt == 32 ? 1 : 2;        // Philox blocks per lane and batch: a batch is nb * lpt <= 32 draws = one 32-bit mask
+        const int lpb = (nb * lpt) >> dsh;       // levels served by one batch (a power of two)
+        uint32_t RP = 0, RB = 0;                 // per draw of the batch: random() < epsilon; the random action
         int cur = 0, a = -1, levels = 0;
-        bool active = valid, expand = false, nan = false;
-        int L = 0;                         // level index, the same for every group of the warp that is still descending
+        bool active = valid, expand = false;
+        uint32_t nanacc = 0;
+        int L = 0;                               // level index, the same for every group of the warp that is still descending
 #pragma unroll 1
         while (__any_sync(FULL, active)) {
-            const int kb = L % lpb;
-            if (kb == 0) {  // draws st.draws + dpl * L + [0, lpt)
-                const uint32_t x = philox_draw_x(k0, k1, tlo, thi, (uint32_t)(st.draws + dpl * L + gl));
-                const bool lt = (double)u32_to_unit(x) < p.epsilon;
-                RP = __ballot_sync(FULL, lt) >> gbase;
+            const int kb = L & (lpb - 1);
+            if (kb == 0) {  // draws st.draws + (L << dsh) + [0, nb * lpt): lane gl generates draws gl and lpt + gl of the batch
+                const uint32_t d0 = (uint32_t)(st.draws + (L << dsh) + gl);
+                const uint32_t x = philox_draw_x(k0, k1, tlo, thi, d0);
+                RP = __ballot_sync(FULL, (double)u32_to_unit(x) < epsilon) >> gbase;
                 RB = __ballot_sync(FULL, u32_to_index(x, 2) != 0) >> gbase;
+                if (nb == 2) {
+                    const uint32_t y = philox_draw_x(k0, k1, tlo, thi, d0 + (uint32_t)lpt);
+                    const uint32_t lo_mask = (1u << lpt) - 1u;
+                    RP = (RP & lo_mask) | ((__ballot_sync(FULL, (double)u32_to_unit(y) < epsilon) >> gbase) << lpt);
+                    RB = (RB & lo_mask) | ((__ballot_sync(FULL, u32_to_index(y, 2) != 0) >> gbase) << lpt);
+                }
+                if (!eps) RP = 0;
             }
+            // one 16-byte piece per level: child[0] | child[1] << 16, parent | paction << 16 | flags << 24, cached rule, -
+            const uint4 q3 = ds_lds128(rows_s + 64u * cur + 48u);
+            const int sh = kb << dsh;
+            const uint32_t rbit = (RB >> (sh + dsh)) & 1u;
+            const bool use_r = (((RP >> sh) | (q3.z >> 1)) & 1u) != 0;   // epsilon pick, or equal scores: the random action
+            const int an = (int)(use_r ? rbit : (q3.z & DS_DEC_A));
+            const int child = (int)(an ? (q3.x >> 16) : (q3.x & 0xFFFFu));
             if (active) {
-                const uint4 q3 = reinterpret_cast<const uint4*>(rows + cur)[3];  // child[0] | child[1] << 16, parent | paction | flags, rule, -
-                if (L > 0 && ((q3.y >> 24) & ROW_TERMINAL)) {  // trace ends on an existing terminal node
+                if ((q3.y >> 24) & ROW_TERMINAL) {  // trace ends on an existing terminal node (the root never is one)
                     a = -1;
                     active = false;
                 } else {
-                    const bool rpick = eps && ((RP >> (2 * kb)) & 1u);
-                    const int rbit = (int)((RB >> (dpl * kb + dpl - 1)) & 1u);
-                    a = (rpick || (q3.z & DS_DEC_TIE)) ? rbit : (int)(q3.z & DS_DEC_A);
-                    nan |= (q3.z & DS_DEC_NAN) != 0;
-                    if (gl == 0) path[L] = (uint16_t)((cur << 1) | a);
+                    a = an;
+                    nanacc |= q3.z;
+                    if (gl == 0) ds_sts16(path_s + 2u * L, (uint32_t)((cur << 1) | an));
                     ++levels;
-                    const int child = (int)(a ? (q3.x >> 16) : (q3.x & 0xFFFFu));
                     if (child == DROW_NONE) { active = false; expand = true; }
                     else cur = child;
                 }
             }
             ++L;
         }
+        DSP_STAMP(2);
+#ifdef AZG_TREE_PROF
+        if (threadIdx.x == 0) cx.prof[7] += (unsigned long long)L;
+#endif
         if (valid && gl == 0) {
-            if (nan) atomicOr(p.err, ERR_NAN);
-            st.draws += dpl * levels;
+            if (nanacc & DS_DEC_NAN) atomicOr(cx.err, ERR_NAN);
+            st.draws += levels << dsh;
             st.levels += (uint32_t)levels;
             st.depth = (uint16_t)levels;
             if (expand) {
                 const int child = st.n_rows;
-                if (child >= p.R) {
-                    atomicOr(p.err, ERR_CAPACITY);
+                if (child >= R) {
+                    atomicOr(cx.err, ERR_CAPACITY);
                     sm.leaf[i] = cur;
                     st.depth = 0;
                 } else {
                     st.n_rows = child + 1;
-                    const double* sp = p.dstate + ((size_t)t * p.R + cur) * 4;
+                    const double* sp = cx.dstate + ((size_t)i * R + cur) * 4;
                     const double s[4] = {sp[0], sp[1], sp[2], sp[3]};
                     double o[4], rew;
                     const bool term = env::cartpole_step(s, a, o, rew);
-                    double* so = p.dstate + ((size_t)t * p.R + child) * 4;
+                    double* so = cx.dstate + ((size_t)i * R + child) * 4;
                     so[0] = o[0]; so[1] = o[1]; so[2] = o[2]; so[3] = o[3];
                     DRow nr;
                     nr.W[0] = nr.W[1] = 0.0;
@@ -489,7 +554,24 @@ __device__ __forceinline__ void ds_step(const TreeParams& p, const Tabs& tb, con
             sm.st[i] = st;
         }
         __syncwarp();
+        DSP_STAMP(4);
     }
+}
+
+// The tree phase of the whole-search kernel (qmlp2.cuh TSM): called by every thread of the 16 epilogue warps; mode bit 0 = backup
+// of the finished simulation, bit 1 = descent + expansion of the next.  Everything it needs comes out of the DsCtx copy, so the
+// level loop holds its addresses in registers (as a NOINLINE function it measured slower: 235 against 295 M sims/s, r2k).
+#ifdef AZG_DS_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void ds_phase(const DsCtx* cxs, int mode) {
+    const DsCtx cx = *cxs;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int i = tid / cx.lpt;
+    if ((tid & ~31) / cx.lpt >= cx.ntrees) return;  // no tree on this warp
+    ds_step(cx, i, i < cx.ntrees, lane, (mode & 1) != 0, (mode & 2) != 0);
 }
 
 // end of the search: rows in use and per-tree scalars back to the global tables (cooperatively, `nthreads` threads of the CTA)
