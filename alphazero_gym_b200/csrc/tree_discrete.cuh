@@ -341,7 +341,7 @@ __device__ __forceinline__ uint32_t ds_decide(const DsCtx& cx, double W0, double
     const double pc0 = cx.puct_f32 ? (double)__fmul_rn(pr0, cuf) : (double)pr0 * cx.c_uct;
     const double pc1 = cx.puct_f32 ? (double)__fmul_rn(pr1, cuf) : (double)pr1 * cx.c_uct;
     double u0, u1;
-    if (nn <= cx.tabn && n0 < cx.tabn && n1 < cx.tabn && (n0 == 0 || div_tab_ok(W0)) && (n1 == 0 || div_tab_ok(W1))) {
+    if (nn <= cx.tabn && (unsigned)n0 < (unsigned)nn && (unsigned)n1 < (unsigned)nn && (n0 == 0 || div_tab_ok(W0)) && (n1 == 0 || div_tab_ok(W1))) {
         const double sq = cx.sq[nn];
         const double q0 = div_tab(W0, n0 > 0 ? n0 : 1, cx.rcp), q1 = div_tab(W1, n1 > 0 ? n1 : 1, cx.rcp);
         const double e0 = div_tab(sq, n0 + 1, cx.rcp), e1 = div_tab(sq, n1 + 1, cx.rcp);
@@ -432,11 +432,16 @@ __device__ __forceinline__ void ds_step(const DsCtx& cx, int i, bool valid, int 
             const int nlev = __reduce_max_sync(FULL, top);           // largest over the warp's groups
             double myR = 0.0;
 #pragma unroll 1
-            for (int sl = nlev - 1; sl >= 0; --sl) {
-                const double rq = __shfl_sync(FULL, rj, gbase + sl);
-                if (sl < top) {
-                    Rv = rq + gamma * Rv;
-                    if (sl == gl) myR = Rv;
+            for (int sb = (nlev - 1) & ~3; sb >= 0; sb -= 4) {  // four levels per round: the shuffles do not wait for the chain
+                double rq[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) rq[k] = __shfl_sync(FULL, rj, (gbase + sb + k) & 31);
+#pragma unroll
+                for (int k = 3; k >= 0; --k) {
+                    if (sb + k < top) {
+                        Rv = rq[k] + gamma * Rv;
+                        if (sb + k == gl) myR = Rv;
+                    }
                 }
             }
             if (act) {
@@ -492,19 +497,16 @@ __device__ __forceinline__ void ds_step(const DsCtx& cx, int i, bool valid, int 
             const bool use_r = (((RP >> sh) | (q3.z >> 1)) & 1u) != 0;   // epsilon pick, or equal scores: the random action
             const int an = (int)(use_r ? rbit : (q3.z & DS_DEC_A));
             const int child = (int)(an ? (q3.x >> 16) : (q3.x & 0xFFFFu));
-            if (active) {
-                if ((q3.y >> 24) & ROW_TERMINAL) {  // trace ends on an existing terminal node (the root never is one)
-                    a = -1;
-                    active = false;
-                } else {
-                    a = an;
-                    nanacc |= q3.z;
-                    if (gl == 0) ds_sts16(path_s + 2u * L, (uint32_t)((cur << 1) | an));
-                    ++levels;
-                    if (child == DROW_NONE) { active = false; expand = true; }
-                    else cur = child;
-                }
-            }
+            // branch-free: `term` = the trace ends on an existing terminal node (the root never is one), `go` = this level is descended
+            const bool term = ((q3.y >> 24) & ROW_TERMINAL) != 0;
+            const bool go = active && !term;
+            a = go ? an : (active ? -1 : a);
+            nanacc |= go ? q3.z : 0u;
+            if (go && gl == 0) ds_sts16(path_s + 2u * L, (uint32_t)((cur << 1) | an));
+            levels += go ? 1 : 0;
+            expand = expand || (go && child == DROW_NONE);
+            active = go && child != DROW_NONE;
+            cur = active ? child : cur;
             ++L;
         }
         DSP_STAMP(2);
