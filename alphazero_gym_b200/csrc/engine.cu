@@ -79,6 +79,7 @@ struct azg_engine {
     float* qfl = nullptr;
     int qfl_count = 0;
     size_t qmlp_smem = 0;
+    int last_fused_kind = 0;        // whole-search kernel of the last search: 1 two-phase, 2 warpgroups, 3 two-phase with the trees in shared memory
     size_t smem_optin = 0;
     size_t tsm_smem_max = 0;        // discrete whole-search kernel with the trees in shared memory (qmlp2.cuh TSM): dynamic shared memory it may use
     bool q8 = false;
@@ -604,6 +605,7 @@ static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const
                 qmlp2_tsm_smem_bytes(NL, e->qfl_count, per, p.R) <= e->tsm_smem_max)
                 tsm_per = per;
         }
+        const_cast<azg_engine*>(e)->last_fused_kind = tsm_per ? 3 : (two_phase ? 1 : 2);
         if (tsm_per) {
             if constexpr (S == 4) {
                 const int grid = (hi - lo + tsm_per - 1) / tsm_per;
@@ -1075,6 +1077,7 @@ extern "C" int azg_fused_stats(azg_engine* e, int64_t out[8]) {
             "discrete level loop: scores %llu draw+pick %llu next row %llu over %llu warp-levels\n", h[8], h[9], h[10], h[11], h[12], h[0], h[4], h[13], h[14], h[11], h[15]);
 #endif
     for (int k = 0; k < 8; ++k) out[k] = (int64_t)h[k];
+    out[5] = e->last_fused_kind;
     return AZG_OK;
 }
 

@@ -102,6 +102,17 @@ __device__ __forceinline__ void phase_sync(uint64_t* bar, uint32_t& parity) {
     mbar_wait(bar, parity);
     parity ^= 1u;
 }
+// the same for a warp that has nothing to do for a whole phase (the post-processing warps during the tree phase): it sleeps between
+// polls instead of competing with the tree warps of its scheduler for issue slots
+__device__ __forceinline__ void phase_sync_idle(uint64_t* bar, uint32_t& parity) {
+    mbar_arrive(bar);
+#ifndef AZG_NO_IDLE_SLEEP
+    while (!mbar_try_wait(bar, parity)) __nanosleep(256);
+#else
+    mbar_wait(bar, parity);
+#endif
+    parity ^= 1u;
+}
 
 // per-CTA constants of the epilogue warps
 struct Q2Ctx {
@@ -303,7 +314,13 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
         cx.k0 = (uint32_t)seed; cx.k1 = (uint32_t)(seed >> 32);
         cx.tree0 = tree_base(tp) + row_begin;
         cx.tabn = FUSED_TAB; cx.R = tp.R; cx.puct_f32 = tp.puct_f32; cx.ntrees = nrows;
-        cx.lpt = nrows <= 16 ? 32 : (nrows <= 32 ? 16 : (nrows <= 64 ? 8 : 4));  // a group of lpt consecutive lanes per tree: 28 trees = 28 half warps
+        // a group of lpt consecutive lanes per tree.  Measured at 28 trees per CTA (profiles/README.md r2n): lpt = 16 (14 warps) 320,
+        // lpt = 8 (7 warps) 337, lpt = 4 (4 warps) 318 M sims/s -- fewer warps issue fewer instructions in total (both halves of
+        // a warp share one stream), more lanes per tree shorten the backup and the draw generation
+        cx.lpt = nrows <= 64 ? 8 : 4;
+#ifdef AZG_TSM_LPT
+        cx.lpt = AZG_TSM_LPT;
+#endif
         cx.pad = 0;
         cx.prof = s_dsprof;
         for (int k = 0; k < 8; ++k) s_dsprof[k] = 0;
@@ -386,7 +403,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
         }
         if (FUSED) {
             phase_sync(&phase_bar, pph);  // every row of this evaluation is finished: the tree phase may start
-            phase_sync(&phase_bar, pph);  // the tree phase is over: leaf words and X of the next simulation are in place
+            phase_sync_idle(&phase_bar, pph);  // the tree phase is over: leaf words and X of the next simulation are in place
         }
         }
         if (nev && p.mode == 0) p.evals[ev_row] += nev;  // only the total over trees is reported (azg_get_counters)

@@ -272,8 +272,9 @@ class SearchEngine:
         arr = (C.c_int64 * 8)()
         check(self._lib.azg_fused_stats(self._h, C.byref(arr)))
         tot = max(1, int(arr[0]))
+        kind = {1: "two_phase", 2: "warpgroups", 3: "two_phase_trees_in_shared_memory"}.get(int(arr[5]), "none")
         return {"ctas": int(arr[4]), "kernel_cycles_per_cta": tot / max(1, int(arr[4])), "tree_phase": arr[1] / tot,
-                "wait_for_post_processing": arr[2] / tot, "x_wait_mma": arr[3] / tot}
+                "wait_for_post_processing": arr[2] / tot, "x_wait_mma": arr[3] / tot, "kernel": kind}
 
     # ---- standalone kernels (known-answer tests) ---------------------------------------------------------
     def mlp_forward(self, x: np.ndarray):

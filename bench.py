@@ -483,15 +483,16 @@ def measure(ctx: Ctx, args, name: str, trees_per_gpu=None, scaling: str = "weak"
                     tr_bytes = json.load(f).get(name, {}).get("k_search")
                 tr_how += "; value from profiles/traffic.json (an earlier ncu capture)" if tr_bytes else ""
         tree_s, slot_s, mma_s = st["tree_phase"], st["wait_for_post_processing"], st.get("x_wait_mma", 0.0)
-        two_phase = B < 3 * 128 * sm_count and os.environ.get("AZG_FUSED_KERNEL", "")[:1] != "w"  # engine.cu launch_fused_t picks by batch size
-        if os.environ.get("AZG_FUSED_KERNEL", "")[:1] == "t" or os.environ.get("AZG_FUSED_V1"):
-            two_phase = True
+        two_phase = st["kernel"] != "warpgroups"  # engine.cu launch_fused_t picks by batch size
+        tsm = st["kernel"] == "two_phase_trees_in_shared_memory"
         wg_time = ({"evaluation_phases": 1.0 - tree_s, "tree_phases": tree_s, "evaluation_warps_waiting_for_row_finish": slot_s,
                     "source": "in-kernel cycle counters (azg_fused_stats), CTA average; the two phases alternate for the whole CTA"} if two_phase else
                    {"evaluation_with_tmem_slot": 1.0 - tree_s - slot_s, "of_which_waiting_for_mma": mma_s, "tree_step_and_row_finish": tree_s,
                     "waiting_for_a_tmem_slot": slot_s, "source": "in-kernel cycle counters (azg_fused_stats), average over warpgroups"})
         dominant = {
-            "kernel": ("k_qmlp2<FUSED> (whole search in one persistent kernel, thin batches: per simulation an evaluation phase on tcgen05 kind::i8 with "
+            "kernel": ("k_qmlp2<FUSED, TSM> (whole search in one persistent kernel, the CTA's trees resident in SHARED MEMORY for the whole search: "
+                       "per simulation an evaluation phase on tcgen05 kind::i8 and a tree phase with a group of 8 lanes per tree)" if tsm else
+                       "k_qmlp2<FUSED> (whole search in one persistent kernel, thin batches: per simulation an evaluation phase on tcgen05 kind::i8 with "
                        "16 warps per tile pair and a tree phase, one thread per tree)" if two_phase else
                        "k_search_wg (whole search in one persistent kernel; four independent warpgroups per SM, a thread owns its tree's step "
                        "and its row of the tcgen05 kind::i8 evaluation)"),
@@ -503,8 +504,11 @@ def measure(ctx: Ctx, args, name: str, trees_per_gpu=None, scaling: str = "weak"
             "hbm": {"algorithmic_bytes_per_launch": tbytes, "algorithmic_gbs": tbytes / (k_ms * 1e-3) / 1e9,
                     "frac_of_hbm_peak": tbytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                     "traffic_over_algorithmic": (tr_bytes / tbytes) if tr_bytes else None,
-                    "note": "select + backup + expansion bytes (SURVEY 8d formula from the engine's own counters) over the WHOLE kernel's time: "
-                            "the tree step overlaps the evaluation of other warpgroups, so it has no time of its own"},
+                    "note": ("select + backup + expansion bytes (SURVEY 8d formula from the engine's own counters) over the WHOLE kernel's time; "
+                             "in this kernel they are served from shared memory (the rows reach HBM once, when the search ends), so the HBM "
+                             "roofline does not bound it" if tsm else
+                             "select + backup + expansion bytes (SURVEY 8d formula from the engine's own counters) over the WHOLE kernel's time: "
+                             "the tree step overlaps the evaluation of other warpgroups, so it has no time of its own")},
             "time_split": wg_time,
         }
         roof_all = {"whole_search_kernel": dominant}

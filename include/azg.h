@@ -72,11 +72,15 @@ typedef struct azg_config {
                                 Deterministic and bit-reproducible by the CPU oracle (AZO_EVAL_Q8); V error vs an f64
                                 evaluation is ~2x that of the FP32 path, well inside the 1e-5 parity tolerance. */
 
-#define AZG_FLAG_FUSED 4u    /* continuous variant with AZG_FLAG_EVAL_Q8: run the whole search (root evaluation, every simulation's
-                                backup + select + expansion + leaf evaluation) in ONE persistent kernel per chunk of trees; a CTA
-                                owns its trees for the whole search and overlaps the tree walk of one tile pair with the
-                                evaluation of the other.  Same arithmetic, same results bit for bit as the per-simulation
-                                launches. */
+#define AZG_FLAG_FUSED 4u    /* with AZG_FLAG_EVAL_Q8, both variants (CartPole and Pendulum): run the whole search (root evaluation, every
+                                simulation's backup + select + expansion + leaf evaluation) in ONE persistent kernel per chunk of
+                                trees; a CTA owns its trees for the whole search.  Three kernels, chosen by batch size and variant
+                                (engine.cu launch_fused_t; azg_fused_stats out[5] says which ran): four independent warpgroups per SM,
+                                each thread owning its tree's step and its row of the evaluation (>= 3 full tiles per SM); a CTA
+                                alternating an evaluation phase and a tree phase (thinner batches); and, for the discrete tree, the
+                                same with the CTA's trees RESIDENT IN SHARED MEMORY for the whole search when they fit (BASELINE
+                                config 3: 28 CartPole trees per SM).  Same arithmetic, same results bit for bit as the
+                                per-simulation launches. */
 
 #define AZG_FLAG_RNG_MT19937 8u /* un-shimmed compatibility: every random number comes from the generators the reference itself uses,
                                    seeded per tree at the start of every search like random.seed(seed + global tree id) and
@@ -224,7 +228,8 @@ int azg_get_counters(azg_engine* e, int32_t B, int64_t out[8]);
 
 /* Cycle accounting of the whole-search kernel (AZG_FLAG_FUSED) since the last call, summed over CTAs, then reset (measured on
  * thread 0 of each CTA): out[0] kernel cycles, out[1] cycles in the tree phases (backup + select + expansion of every tree of the
- * CTA, up to the closing barrier), out[2] cycles waiting for the post-processing warps before a tree phase, out[4] CTAs counted.
+ * CTA, up to the closing barrier), out[2] cycles waiting for the post-processing warps before a tree phase, out[4] CTAs counted,
+ * out[5] which whole-search kernel the last search ran (1 two-phase, 2 warpgroups, 3 two-phase with the trees in shared memory).
  * Synchronises the device. */
 int azg_fused_stats(azg_engine* e, int64_t out[8]);
 
