@@ -585,7 +585,16 @@ static cudaError_t launch_qmlp_t(const azg_engine* e, const MlpParams& m, cudaSt
 // whole-search kernel (AZG_FLAG_FUSED): one persistent launch per chunk of at most sm_count x Q2_MAX_TILES x 128 trees
 template <int S, int ACT, int NL>
 static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const TreeParams& p, int N, cudaStream_t st, int* launches) {
-    const int chunk = e->sm_count * Q2_MAX_TILES * 128;
+    int chunk = e->sm_count * Q2_MAX_TILES * 128;
+    if constexpr (S == 4) {
+        // Discrete search: up to two full waves of shared-memory-resident trees (cap per SM x SMs each) beat the two-phase kernel on
+        // rows in HBM, whose simulation takes 32 us whatever the batch (measured, profiles/README.md r2p: 8192 trees 248 M sims/s
+        // there against 2 x 4096 at 337 M) -- so such a batch is cut into equal chunks, one launch each
+        int cap = 0;
+        while (cap < 128 && qmlp2_tsm_smem_bytes(NL, e->qfl_count, cap + 1, p.R) <= e->tsm_smem_max) ++cap;
+        const long long wave = (long long)cap * e->sm_count;
+        if (cap > 0 && !p.rng_mt && !getenv("AZG_NO_TSM") && e->fused_mode != 2 && p.B > wave && p.B <= 2 * wave) chunk = (p.B + 1) / 2;
+    }
     for (int lo = 0; lo < p.B; lo += chunk) {
         const int hi = std::min(p.B, lo + chunk);
         cudaError_t ce;

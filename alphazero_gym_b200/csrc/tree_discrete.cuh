@@ -403,7 +403,6 @@ __device__ __forceinline__ void ds_sts16(uint32_t a, uint32_t v) { asm volatile(
 __device__ __forceinline__ void ds_step(const DsCtx& cx, int i, bool valid, int lane, const bool BACKUP, const bool SELECT) {
     const uint32_t FULL = 0xFFFFFFFFu;
     DSP_BEGIN();
-    if (!valid) i = 0;  // lanes without a tree read tree 0's tables and write nothing
     const SmTrees sm = cx.sm;
     const int lpt = cx.lpt, R = cx.R;
     DRow* rows = sm.rows + (size_t)i * R;
@@ -513,6 +512,7 @@ __device__ __forceinline__ void ds_step(const DsCtx& cx, int i, bool valid, int 
 #ifdef AZG_TREE_PROF
         if (threadIdx.x == 0) cx.prof[7] += (unsigned long long)L;
 #endif
+        __syncwarp();  // every lane has read the tree's scalars and rows before lane 0 of its group rewrites them
         if (valid && gl == 0) {
             if (nanacc & DS_DEC_NAN) atomicOr(cx.err, ERR_NAN);
             st.draws += levels << dsh;
@@ -571,9 +571,10 @@ __device__ __forceinline__
 void ds_phase(const DsCtx* cxs, int mode) {
     const DsCtx cx = *cxs;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int i = tid / cx.lpt;
-    if ((tid & ~31) / cx.lpt >= cx.ntrees) return;  // no tree on this warp
-    ds_step(cx, i, i < cx.ntrees, lane, (mode & 1) != 0, (mode & 2) != 0);
+    const int i = tid / cx.lpt, i0 = (tid & ~31) / cx.lpt;  // this lane's tree; the first tree of its warp
+    if (i0 >= cx.ntrees) return;  // no tree on this warp
+    // lanes without a tree shadow the warp's first tree (they read what its lanes read, at the same points, and write nothing)
+    ds_step(cx, i < cx.ntrees ? i : i0, i < cx.ntrees, lane, (mode & 1) != 0, (mode & 2) != 0);
 }
 
 // end of the search: rows in use and per-tree scalars back to the global tables (cooperatively, `nthreads` threads of the CTA)
