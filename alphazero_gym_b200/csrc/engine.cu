@@ -1085,6 +1085,11 @@ extern "C" int azg_fused_stats(azg_engine* e, int64_t out[8]) {
     fprintf(stderr, "tree step sections (cycles summed over warps): load %llu backup %llu select %llu insert %llu expand+store %llu | per-WG total %llu over %llu warpgroups | "
             "discrete level loop: scores %llu draw+pick %llu next row %llu over %llu warp-levels\n", h[8], h[9], h[10], h[11], h[12], h[0], h[4], h[13], h[14], h[11], h[15]);
 #endif
+#ifdef AZG_EVAL_PROF
+    fprintf(stderr, "evaluation timeline of epilogue thread 0, cycles per CTA and search: layer 0 %llu | MMA wait %llu | load + convert %llu | stash / quantise / heads %llu | "
+            "post-processing wait %llu | tree phase %llu | kernel %llu\n", h[8] / (h[4] ? h[4] : 1), h[9] / (h[4] ? h[4] : 1), h[10] / (h[4] ? h[4] : 1), h[11] / (h[4] ? h[4] : 1),
+            h[12] / (h[4] ? h[4] : 1), h[13] / (h[4] ? h[4] : 1), h[0] / (h[4] ? h[4] : 1));
+#endif
     for (int k = 0; k < 8; ++k) out[k] = (int64_t)h[k];
     out[5] = e->last_fused_kind;
     return AZG_OK;

@@ -472,6 +472,15 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
             }
             phase_sync(&phase_bar, pph);
         }
+#ifdef AZG_EVAL_PROF
+        // timeline of the evaluation phase on epilogue thread 0: [0] layer 0 + quantise, [1] wait for the MMAs, [2] accumulator loads +
+        // conversion + activation, [3] stash / quantise / heads, [4] wait for the post-processing warps, [5] tree phase
+        long long ep_last = clock64();
+#define EP_STAMP(k) do { const long long _t = clock64(); if (tid == 0) s_dsprof[k] += (unsigned long long)(_t - ep_last); ep_last = _t; } while (0)
+        if (!TSM && tid == 0) for (int k = 0; k < 8; ++k) s_dsprof[k] = 0;
+#else
+#define EP_STAMP(k)
+#endif
         uint32_t fullph = 0;  // bit T: parity of the next wait on full[T]
         uint32_t hfph = 0;    // bit T: parity of the next wait on hfree[T]
 #pragma unroll 1
@@ -487,6 +496,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
                 const float cx = q2_layer0<S, ACT>(c, p, T, c.lg * 32 < nv, row0 + c.r, c.r < nv);
                 if (T == 0) cx0 = cx; else cx1 = cx;
             }
+            EP_STAMP(0);
 #pragma unroll 1
             for (int step = 0; step < NL * 2 * nt; ++step) {
                 // step -> (layer, half, tile), tile fastest; nt is 1 or 2
@@ -498,6 +508,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
                 mbar_wait(full + T, (fullph >> T) & 1u);
                 fullph ^= 1u << T;
                 tc_fence_after();
+                EP_STAMP(1);
                 const uint32_t lane_base = tb + ((uint32_t)(c.lg * 32) << 16);
                 const uint32_t stash = lane_base + Q2_SCRATCH_COL + T * 64 + c.cq * 16;
                 float v[16];
@@ -535,6 +546,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
                     tc_fence_before();
                     if (h == 0) mbar_arrive(freeb + T);
                 }
+                EP_STAMP(2);
                 if (h == 0) {
                     if (l == 0 && (t0 > 0 || s > 0)) {  // the slot's scratch still holds the head partial sums of its previous tile
                         mbar_wait(hfree + T, (hfph >> T) & 1u);
@@ -560,6 +572,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
                         q2_heads(c, p, T, wact, u, v);
                     }
                 }
+                EP_STAMP(3);
             }
         }
         if (FUSED) {
@@ -583,6 +596,10 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
             phase_sync(&phase_bar, pph);
             cyc_sync += c1 - c0;
             cyc_tree += clock64() - c1;
+#ifdef AZG_EVAL_PROF
+            if (tid == 0) { s_dsprof[4] += (unsigned long long)(c1 - c0); s_dsprof[5] += (unsigned long long)(clock64() - c1); }
+            ep_last = clock64();
+#endif
         }
         }
         if (TSM) ds_writeback(tp, smt, nrows, row_begin, tid, Q2_EPI_THREADS);  // after the last phase boundary: the rows are final
@@ -593,6 +610,9 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
             atomicAdd(p.stats + 4, 1ull);
 #ifdef AZG_TREE_PROF
             if (TSM) for (int k = 0; k < 8; ++k) atomicAdd(p.stats + 8 + k, s_dsprof[k]);
+#endif
+#ifdef AZG_EVAL_PROF
+            for (int k = 0; k < 8; ++k) atomicAdd(p.stats + 8 + k, s_dsprof[k]);
 #endif
         }
     }
