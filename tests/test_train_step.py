@@ -4,7 +4,8 @@ The goldens (tests/golden/train_*.npz) come from oracle/gen_train_golden.py, whi
 DiscreteAgent.update of /root/reference with its own policies, losses and torch optimizers for three consecutive steps.
 Bar: every loss component within 1e-5 relative (+1e-6 absolute) at every step; final weights within 2e-6 absolute (the
 optimizers divide by sqrt(v) + eps with eps = 1e-10 / 1e-7, so a last-bit difference in a near-zero gradient is a visible
-difference in the step: at most 0.1 % of the weights may deviate more, and none by more than two learning-rate steps).
+difference in the step: on the GPU, where cuBLAS sums in another order, at most 0.1 % of the weights may deviate more, none by more
+than two learning-rate steps, and the update of every other weight must agree in sign and within 5 %; on the CPU no weight may).
 """
 import os
 
@@ -50,15 +51,24 @@ def _run(name, device, cuda_graph=False):
     return g, tr, infos
 
 
-def _check(name, device, loss_rtol, w_atol, cuda_graph=False):
+def _check(name, device, loss_rtol, w_atol, cuda_graph=False, outliers=0.0):
+    """outliers: fraction of the weights allowed beyond w_atol.  0 on the CPU (same kernels, same summation order as the reference:
+    measured max deviation 2e-7).  On the GPU cuBLAS sums the GEMMs in another order, and RMSprop / Adam divide by sqrt(v) + eps with
+    eps = 1e-10 / 1e-7: a last-bit difference in a near-zero gradient is a full-size step, so up to 0.1 % of the weights may differ,
+    each by at most two learning-rate steps -- and the UPDATE of every other weight must agree with the reference's in sign and size."""
     g, tr, infos = _run(name, device, cuda_graph)
     for s, info in enumerate(infos):
         for k, v in info.items():
             ref = float(g[f"info_{k}_{s}"])
             assert abs(v - ref) <= loss_rtol * abs(ref) + 1e-6, (name, s, k, v, ref)
-    w, ref = tr.flat_weights().cpu().numpy(), g["w_3"]
+    w, ref, w0 = tr.flat_weights().cpu().numpy(), g["w_3"], g["w0"]
     d = np.abs(w - ref)
-    assert (d > w_atol).mean() <= 1e-3 and d.max() <= 2.5e-3, (name, float((d > w_atol).mean()), float(d.max()))
+    far = d > w_atol
+    assert far.mean() <= outliers and d.max() <= (2.5e-3 if outliers else w_atol), (name, float(far.mean()), float(d.max()))
+    dw, dw_ref = (w - w0)[~far], (ref - w0)[~far]
+    moved = np.abs(dw_ref) > 10 * w_atol
+    assert np.all(np.sign(dw[moved]) == np.sign(dw_ref[moved]))
+    assert np.all(np.abs(dw[moved] - dw_ref[moved]) <= 0.05 * np.abs(dw_ref[moved]) + w_atol)
     if "log_alpha_3" in g.files:
         assert abs(float(tr.loss.log_alpha.detach()) - float(g["log_alpha_3"])) <= 1e-6
 
@@ -73,7 +83,7 @@ def test_update_matches_reference_cpu(name):
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_update_matches_reference_gpu(name):
     """The same step on cuda:0 (cuBLAS GEMMs sum in a different order: losses within 1e-4, weights within 2e-5)."""
-    _check(name, "cuda:0", 1e-4, 2e-5)
+    _check(name, "cuda:0", 1e-4, 2e-5, outliers=1e-3)
 
 
 @pytest.mark.gpu
@@ -81,7 +91,7 @@ def test_update_matches_reference_gpu(name):
 def test_graph_captured_update_matches_reference_gpu(name):
     """The whole step replayed from a CUDA graph (Trainer(cuda_graph=True)): three replays = the reference's three steps, i.e. the
     warm-up steps of the capture leave no trace in weights or optimizer state."""
-    _check(name, "cuda:0", 1e-4, 2e-5, cuda_graph=True)
+    _check(name, "cuda:0", 1e-4, 2e-5, cuda_graph=True, outliers=1e-3)
 
 
 @pytest.mark.gpu
