@@ -27,7 +27,7 @@ EXPORTS = [
     "azg_search_discrete", "azg_search_continuous", "azg_cmax", "azg_root_results", "azg_search_host", "azg_status",
     "azg_rows", "azg_set_tapes", "azg_dump_tree_discrete", "azg_dump_tree_continuous", "azg_get_counters",
     "azg_head_dim", "azg_mlp_forward", "azg_env_step", "azg_profile_search", "azg_set_seed", "azg_selfplay_seed",
-    "azg_selfplay_step", "azg_fused_stats", "azg_search_host_begin", "azg_search_host_end",
+    "azg_selfplay_step", "azg_fused_stats", "azg_search_host_begin", "azg_search_host_end", "azg_set_reward_model",
 ]
 
 
@@ -106,6 +106,7 @@ def load():
     L.azg_mlp_forward.restype, L.azg_mlp_forward.argtypes = C.c_int, [vp, i32, vp, vp, vp, vp]
     L.azg_env_step.restype, L.azg_env_step.argtypes = C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.azg_set_seed.restype, L.azg_set_seed.argtypes = C.c_int, [vp, C.c_uint64, vp]
+    L.azg_set_reward_model.restype, L.azg_set_reward_model.argtypes = C.c_int, [vp, C.c_double, C.c_double]
     L.azg_selfplay_seed.restype, L.azg_selfplay_seed.argtypes = C.c_uint64, [C.c_uint64, i64]
     L.azg_selfplay_step.restype = C.c_int
     L.azg_selfplay_step.argtypes = [vp, i32, C.POINTER(SelfPlayIO), i32, i64, i64, C.c_uint64, i32, i32, i32, C.c_double, vp]

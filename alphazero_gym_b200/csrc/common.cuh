@@ -99,6 +99,7 @@ struct TreeParams {
     int32_t B, R, A, K, HS;  // trees, rows per tree, actions, mixture components, head stride (floats)
     int32_t puct_f32, v_target, use_tape;
     double c_uct, gamma, epsilon;
+    double reward_step, reward_terminal;  // CartPole reward of a step / of the terminating step (1.0 / 1.0; rl/wrappers.py -> azg_set_reward_model)
     float gamma_f32, action_bound;
     const uint64_t* seedp;  // Philox key, read from device memory so that azg_set_seed re-keys a captured graph
     int64_t tree_id0;

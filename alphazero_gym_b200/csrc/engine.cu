@@ -79,6 +79,7 @@ struct azg_engine {
     float* qfl = nullptr;
     int qfl_count = 0;
     size_t qmlp_smem = 0;
+    double reward_step = 1.0, reward_terminal = 1.0;  // azg_set_reward_model (rl/wrappers.py around the searched env)
     int last_fused_kind = 0;        // whole-search kernel of the last search: 1 two-phase, 2 warpgroups, 3 two-phase with the trees in shared memory
     size_t smem_optin = 0;
     size_t tsm_smem_max = 0;        // discrete whole-search kernel with the trees in shared memory (qmlp2.cuh TSM): dynamic shared memory it may use
@@ -502,6 +503,7 @@ static TreeParams make_params(const azg_engine* e, int B, int64_t tree_id0) {
     p.B = B; p.R = e->R; p.A = c.num_actions; p.K = c.num_components; p.HS = e->HS;
     p.puct_f32 = c.puct_f32; p.v_target = c.v_target; p.use_tape = e->tapeV != nullptr;
     p.c_uct = c.c_uct; p.gamma = c.gamma; p.epsilon = c.epsilon;
+    p.reward_step = e->reward_step; p.reward_terminal = e->reward_terminal;
     p.gamma_f32 = (float)c.gamma; p.action_bound = c.action_bound;
     p.seedp = e->d_seed; p.tree_id0 = tree_id0;
     p.drows = e->drows; p.dstate = e->dstate;
@@ -1101,6 +1103,21 @@ extern "C" int azg_set_seed(azg_engine* e, uint64_t seed, void* stream) {
     k_set_seed<<<1, 1, 0, (cudaStream_t)stream>>>(e->d_seed, seed);
     CK(cudaGetLastError());
     e->cfg.seed = seed;
+    return AZG_OK;
+}
+
+extern "C" int azg_set_reward_model(azg_engine* e, double reward_step, double reward_terminal) {
+    if (!e) return fail(AZG_EINVAL, "null engine");
+    if (!(reward_step == reward_step) || !(reward_terminal == reward_terminal) || std::isinf(reward_step) || std::isinf(reward_terminal))
+        return fail(AZG_EINVAL, "rewards must be finite");
+    if (e->cfg.variant != AZG_DISCRETE && (reward_step != 1.0 || reward_terminal != 1.0))
+        return fail(AZG_EINVAL, "the reward model applies to the discrete (CartPole) search");
+    if (reward_step == e->reward_step && reward_terminal == e->reward_terminal) return AZG_OK;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);  // captured launches carry the old constants
+    e->graphs.clear();
+    e->reward_step = reward_step; e->reward_terminal = reward_terminal;
     return AZG_OK;
 }
 

@@ -310,6 +310,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
         cx.err = tp.err;
         cx.rcp = s_rcp; cx.sq = s_sq;
         cx.gamma = tp.gamma; cx.epsilon = tp.epsilon; cx.c_uct = tp.c_uct;
+        cx.reward_step = tp.reward_step; cx.reward_terminal = tp.reward_terminal;
         const uint64_t seed = __ldg(tp.seedp);
         cx.k0 = (uint32_t)seed; cx.k1 = (uint32_t)(seed >> 32);
         cx.tree0 = tree_base(tp) + row_begin;

@@ -198,6 +198,7 @@ __device__ __forceinline__ void d_step(const TreeParams& p, const Tabs& tb, int 
             const double s[4] = {st[0], st[1], st[2], st[3]};
             double o[4], rew;
             const bool term = env::cartpole_step(s, a, o, rew);
+            rew = term ? p.reward_terminal : p.reward_step;  // rl/wrappers.py (1.0 / 1.0 without wrappers)
             double* so = p.dstate + ((size_t)t * p.R + child) * 4;
             so[0] = o[0]; so[1] = o[1]; so[2] = o[2]; so[3] = o[3];
             DRow nr;
@@ -267,6 +268,7 @@ struct __align__(16) DsCtx {
     const double* rcp;   // lookup tables (shared memory): 1 / i, sqrt(i), i <= tabn
     const double* sq;
     double gamma, epsilon, c_uct;
+    double reward_step, reward_terminal;
     uint32_t k0, k1;     // Philox key
     int64_t tree0;       // global id of the CTA's tree 0
     int32_t tabn, R, puct_f32, ntrees, lpt, pad;
@@ -530,6 +532,7 @@ __device__ __forceinline__ void ds_step(const DsCtx& cx, int i, bool valid, int 
                     const double s[4] = {sp[0], sp[1], sp[2], sp[3]};
                     double o[4], rew;
                     const bool term = env::cartpole_step(s, a, o, rew);
+                    rew = term ? cx.reward_terminal : cx.reward_step;  // rl/wrappers.py (1.0 / 1.0 without wrappers)
                     double* so = cx.dstate + ((size_t)i * R + child) * 4;
                     so[0] = o[0]; so[1] = o[1]; so[2] = o[2]; so[3] = o[3];
                     DRow nr;

@@ -182,6 +182,11 @@ class SearchEngine:
         with torch.cuda.device(self.device):
             check(self._lib.azg_status(self._h, self._stream()))
 
+    def set_reward_model(self, reward_step: float = 1.0, reward_terminal: float = 1.0) -> None:
+        """Reward wrappers of rl/wrappers.py around the searched CartPole env (azg_set_reward_model): reward of a step / of the
+        terminating step.  Defaults = the plain env."""
+        check(self._lib.azg_set_reward_model(self._h, float(reward_step), float(reward_terminal)))
+
     # ---- host-buffer path (what MCTS*.search + return_results cost end to end) ---------------------
     def host_buffers(self, B: int) -> Dict[str, np.ndarray]:
         """Page-locked result buffers for search_host(out=...): the engine DMAs into them directly (no staging copy)."""

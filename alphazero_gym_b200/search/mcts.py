@@ -28,23 +28,51 @@ from ..network import describe_model, weights_version
 PENDULUM_R_SCALE = 16.2736044  # reference mcts.py:20 (applied inside the engine)
 
 
-# wrappers rl/make_game.py:71-83 puts around the env for the name suffixes -v0n / r / p / s (rl/wrappers.py:44-155): they change the
-# rewards or observations the search sees, and the engine steps the PLAIN CartPole-v0 / Pendulum-v0 dynamics -- searching through them
-# silently would not be the reference's search, so they are refused (the BASELINE configs use the plain envs)
-_REFUSED_WRAPPERS = ("NormalizeWrapper", "ScaleRewardWrapper", "ReparametrizeWrapper", "PILCOWrapper", "ClipRewardWrapper",
-                     "ScaledObservationWrapper")
+# Wrappers rl/make_game.py:71-83 puts around the env for the name suffixes -v0n / r / p / s (rl/wrappers.py:44-155) change the rewards
+# or observations the search sees, while the engine steps the plain CartPole-v0 / Pendulum-v0 dynamics.  The two reward wrappers that
+# are plain Python arithmetic on CartPole's reward -- ReparametrizeWrapper (-v0r) and ScaleRewardWrapper (-v0s) -- are carried into the
+# engine as its reward model (azg_set_reward_model; `reward_model` below evaluates the wrappers' own expressions); the others --
+# NormalizeWrapper (an sklearn scaler fitted on 10 000 random observations), PILCOWrapper (scipy's multivariate normal pdf),
+# ClipRewardWrapper, ScaledObservationWrapper (Atari), and ScaleRewardWrapper around Pendulum (np.float32 rewards, whose promotion through
+# the backup depends on the numpy version) -- are REFUSED: searching through them silently would not be the reference's search.
+_REWARD_WRAPPERS = ("ReparametrizeWrapper", "ScaleRewardWrapper")
+_REFUSED_WRAPPERS = ("NormalizeWrapper", "PILCOWrapper", "ClipRewardWrapper", "ScaledObservationWrapper")
+
+
+def _wrapper_chain(env):
+    """(base env, names of the reward wrappers around it, outermost first); refuses the wrappers the engine does not implement."""
+    e, seen, names = env, 0, []
+    while hasattr(e, "env") and e is not getattr(e, "env") and seen < 16:  # gym.Wrapper chain (rl/make_game.py:60-62)
+        name = type(e).__name__
+        if name in _REFUSED_WRAPPERS:
+            raise NotImplementedError(f"{name} (rl/wrappers.py) changes what the search sees; the CUDA engine implements the plain "
+                                      "CartPole-v0 / Pendulum-v0 envs, ReparametrizeWrapper and ScaleRewardWrapper, and has no CPU fallback")
+        if name in _REWARD_WRAPPERS:
+            names.append(name)
+        e = e.env
+        seen += 1
+    return getattr(e, "unwrapped", e), names
 
 
 def _unwrap(env):
-    e = env
-    seen = 0
-    while hasattr(e, "env") and e is not getattr(e, "env") and seen < 16:  # gym.Wrapper chain (rl/make_game.py:60-62)
-        if type(e).__name__ in _REFUSED_WRAPPERS:
-            raise NotImplementedError(f"{type(e).__name__} (rl/wrappers.py) changes what the search sees; the CUDA engine implements the plain "
-                                      "CartPole-v0 / Pendulum-v0 envs of run_discrete.yaml / run_continuous.yaml and has no CPU fallback")
-        e = e.env
-        seen += 1
-    return getattr(e, "unwrapped", e)
+    return _wrapper_chain(env)[0]
+
+
+def reward_model(env, variant: int):
+    """(reward_step, reward_terminal) of the env's reward wrappers, innermost applied first, each with the wrapper's own Python
+    expression (rl/wrappers.py:58-105) so that the constants are the reference's bit for bit."""
+    _, names = _wrapper_chain(env)
+    step, terminal = 1.0, 1.0  # gym CartPole-v0 pays 1.0 for every step, the terminating one included
+    for name in reversed(names):
+        if name == "ReparametrizeWrapper":
+            if variant == DISCRETE:  # CartPole: r = -1 if terminal else 0.005; Pendulum falls through unchanged (:88-105)
+                step, terminal = 0.005, -1
+        elif name == "ScaleRewardWrapper":
+            if variant != DISCRETE:
+                raise NotImplementedError("ScaleRewardWrapper around Pendulum returns np.float32(reward / 1000.0); how that promotes through "
+                                          "the backup depends on the numpy version, and the CUDA engine does not restate it")
+            step, terminal = step / 250.0, terminal / 250.0
+    return float(step), float(terminal)
 
 
 def env_hidden_state(env, variant: int) -> np.ndarray:
@@ -190,6 +218,7 @@ class MCTSDiscrete(MCTS):
         if self.root_node.terminal:
             raise ValueError("Can't do tree search from a terminal node")
         eng = self._engine(1)
+        eng.set_reward_model(*reward_model(Env, DISCRETE))
         self._results = eng.search_host(hidden[None], self.n_rollouts, np.array([self.root_node.n], np.int32), tree_id0=self._searches)
         self._searches += 1
         self._tree = eng.dump_tree(1)
@@ -247,6 +276,7 @@ class MCTSContinuous(MCTS):
         obs = self.root_state if self.root_state is not None else np.array([np.cos(hidden[0]), np.sin(hidden[0]), hidden[1]])
         self.root_node = RootNode(np.asarray(obs), n=0, hidden=hidden)
         eng = self._engine(1)
+        eng.set_reward_model(*reward_model(Env, CONTINUOUS))
         self._results = eng.search_host(hidden[None], self.n_rollouts, None, tree_id0=self._searches)
         self._searches += 1
         self.root_node.n = self.n_rollouts

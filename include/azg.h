@@ -149,6 +149,15 @@ int azg_status(azg_engine* e, void* stream);
  * (run_continuous.py:24-25, run_discrete.py:27-28). */
 int azg_set_seed(azg_engine* e, uint64_t seed, void* stream);
 
+/* Reward wrappers of the reference around the CartPole env the discrete search steps (rl/wrappers.py:58-105, selected by the
+ * -v0r / -v0s / -v0rs name suffixes, rl/make_game.py:71-83).  They only change the reward a node is created with (mcts.py:449), and
+ * for CartPole that is a constant per terminal flag: reward_step / reward_terminal = 1.0 / 1.0 without wrappers, 0.005 / -1 with
+ * ReparametrizeWrapper, each / 250.0 with ScaleRewardWrapper (the host computes the constants with the wrappers' own Python
+ * expressions).  Takes effect for searches enqueued after the call (synchronises the device and drops captured graphs when something
+ * changes).  Not implemented, and refused by the drop-in classes: NormalizeWrapper (sklearn scaler), PILCOWrapper (scipy pdf),
+ * ScaleRewardWrapper around Pendulum (it returns np.float32, whose promotion through the backup depends on the numpy version). */
+int azg_set_reward_model(azg_engine* e, double reward_step, double reward_terminal);
+
 /* ---- self-play step (BASELINE config 5) -------------------------------------------------------------
  * One environment step of B independent self-play environments, the body of the reference's episode loop
  * (run_continuous.py:117-142, run_discrete.py:100-122), batched and entirely on the device:

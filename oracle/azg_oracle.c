@@ -804,6 +804,7 @@ static int search_discrete_one(const azo_config* c, const net_t* net, const azo_
             child = t->n_nodes++;
             double rew;
             int term = cartpole_step(c, t->state + node * 4, a, t->state + child * 4, &rew);
+            rew = term ? c->reward_terminal : c->reward_step; /* rl/wrappers.py (1.0 / 1.0 without wrappers) */
             t->parent[child] = node; t->paction[child] = a; t->node_n[child] = 0; t->terminal[child] = term; t->r[child] = rew;
             t->echild[node * A + a] = child;
             d_evaluate(c, net, tp, b, t, child, ctr);

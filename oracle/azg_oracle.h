@@ -83,6 +83,11 @@ typedef struct {
     int32_t eval_mode;     /* AZO_EVAL_* */
     int32_t rng_mode;      /* 0: Philox streams (default); 1 (AZO_RNG_MT19937, discrete search only): CPython's generator, seeded
                               with seed + global tree id at the start of every search (azg_oracle.c "AZO_RNG_MT19937") */
+    /* reward wrappers of rl/wrappers.py around the env the search steps (rl/make_game.py:71-83, name suffixes -v0r / -v0s / -v0rs):
+     * CartPole: the reward of a step is a constant per terminal flag -- 1.0 / 1.0 plain, 0.005 / -1 with ReparametrizeWrapper (:78-105),
+     * / 250.0 with ScaleRewardWrapper (:58-75).  (Pendulum's ScaleRewardWrapper returns np.float32, whose promotion through the backup
+     * depends on the numpy version: not restated.) */
+    double reward_step, reward_terminal; /* discrete search */
 } azo_config;
 #define AZO_RNG_PHILOX 0
 #define AZO_RNG_MT19937 1

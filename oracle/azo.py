@@ -41,6 +41,7 @@ class _Cfg(C.Structure):
         ("c_uct", C.c_double), ("gamma", C.c_double), ("epsilon", C.c_double), ("c_pw", C.c_double), ("kappa", C.c_double),
         ("action_bound", C.c_float), ("log_std_min", C.c_float), ("log_std_max", C.c_float),
         ("seed", C.c_uint64), ("eval_mode", C.c_int32), ("rng_mode", C.c_int32),
+        ("reward_step", C.c_double), ("reward_terminal", C.c_double),
     ]
 
 
@@ -132,12 +133,16 @@ class Config:
     seed: int = 34
     eval_mode: int = 0  # EVAL_FP32 | EVAL_Q8
     rng_mode: int = 0   # RNG_PHILOX | RNG_MT19937 (discrete search: CPython's generator, seeded with seed + tree id per search)
+    # reward wrappers (rl/wrappers.py) around CartPole: reward of a step / of the terminating step
+    reward_step: float = 1.0
+    reward_terminal: float = 1.0
 
     def c(self) -> _Cfg:
         return _Cfg(self.variant, self.n_rollouts, self.num_actions, self.num_components, self.state_dim, self.hidden,
                     self.n_hidden, self.activation, self.math_mode, VT[self.V_target_policy], self.puct_f32,
                     self.use_eval_tape, self.c_uct, self.gamma, self.epsilon, self.c_pw, self.kappa,
-                    self.action_bound, self.log_std_min, self.log_std_max, self.seed, self.eval_mode, self.rng_mode)
+                    self.action_bound, self.log_std_min, self.log_std_max, self.seed, self.eval_mode, self.rng_mode,
+                    self.reward_step, self.reward_terminal)
 
     @property
     def rows(self) -> int:

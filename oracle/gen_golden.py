@@ -62,6 +62,11 @@ CASES = {
     "cartpole_n8_hardswish": dict(cfg=azo.discrete_config(n_rollouts=8, epsilon=0.1, activation=azo.ACT_HARDSWISH), B=8),
     "pendulum_n25_relu6": dict(cfg=azo.continuous_config(n_rollouts=25, activation=azo.ACT_RELU6), B=6),
     "pendulum_n25_silu": dict(cfg=azo.continuous_config(n_rollouts=25, activation=azo.ACT_SILU), B=6),
+    # reward wrappers of rl/wrappers.py around the searched env (rl/make_game.py:71-83 name suffixes -v0r / -v0s / -v0rs): the reference's
+    # own wrapper classes in the reference's order; the tilted roots reach terminal states, where ReparametrizeWrapper pays -1
+    "cartpole_n50_wrap_r": dict(cfg=azo.discrete_config(n_rollouts=50, epsilon=0.1), B=8, modify="r", roots="tilted"),
+    "cartpole_n50_wrap_s_g099": dict(cfg=azo.discrete_config(n_rollouts=50, epsilon=0.1, gamma=0.99), B=8, modify="s"),
+    "cartpole_n200_wrap_rs_terminal": dict(cfg=azo.discrete_config(n_rollouts=200, epsilon=0.1), B=6, modify="rs", roots="tilted"),
     # TRAINED weights: the reference agent after 80 real `update` steps (agents.py:319-389, :539-603; lr 3e-3 so that the activation
     # range moves well away from the default initialisation), then its search -- the case the per-row block exponent of the
     # tensor-core evaluation has to survive
@@ -131,7 +136,11 @@ def generate(name: str) -> str:
     model = trained_model(cfg, case["trained"]) if case.get("trained") else RH.make_model(cfg, weight_seed=34)
     roots = roots_for(case)
     if cfg.variant == azo.DISCRETE:
-        out = RH.run_discrete(cfg, model, roots, second_search=case.get("second_search", False))
+        modify = case.get("modify", "")
+        if modify:  # the constants the engine / oracle are given: the wrappers' own Python expressions (search/mcts.py reward_model)
+            from alphazero_gym_b200.search.mcts import reward_model
+            cfg.reward_step, cfg.reward_terminal = reward_model(RH.wrap_like_make_game(RH.CartPoleEnv(roots[0]), modify), azo.DISCRETE)
+        out = RH.run_discrete(cfg, model, roots, second_search=case.get("second_search", False), modify=modify)
     else:
         out = RH.run_continuous(cfg, model, roots)
     out["weights"] = azo.flatten_state_dict(model.state_dict())

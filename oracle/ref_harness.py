@@ -83,6 +83,11 @@ class CartPoleEnv:
     theta_threshold_radians = 12 * 2 * math.pi / 360
     x_threshold = 2.4
 
+    class _Spec:
+        id = "CartPole-v0"
+
+    spec = _Spec()  # rl/wrappers.py get_name() reads env.spec.id
+
     def __init__(self, state):
         self.state = tuple(float(v) for v in state)
 
@@ -229,8 +234,23 @@ def _gamma_arg(g: float):
 # ---------------------------------------------------------------------------------------------
 # Running the reference + dumping its pointer-linked tree into the oracle's table layout
 # ---------------------------------------------------------------------------------------------
+def wrap_like_make_game(env, modify: str):
+    """The reference's OWN reward wrappers (rl/wrappers.py, imported unmodified) around `env`, in the order of
+    rl/make_game.py:71-83 prepare_control_env: 'r' ReparametrizeWrapper inside, 's' ScaleRewardWrapper outside."""
+    if not modify:
+        return env
+    reference_modules()
+    import rl.wrappers as W  # type: ignore
+    assert set(modify) <= {"r", "s"}, "only the arithmetic reward wrappers are restated by the oracle"
+    if "r" in modify:
+        env = W.ReparametrizeWrapper(env)
+    if "s" in modify:
+        env = W.ScaleRewardWrapper(env)
+    return env
+
+
 def run_discrete(cfg: azo.Config, model, root_states: np.ndarray, tree_id0: int = 0,
-                 second_search: bool = False) -> Dict[str, np.ndarray]:
+                 second_search: bool = False, modify: str = "") -> Dict[str, np.ndarray]:
     """MCTSDiscrete.search per tree.  second_search=True additionally does act-like `forward` on the
     most visited root action and searches again (the root.n carry-over quirk); the dump is
     then of the SECOND search and `root_state`/`root_n_init` describe its root."""
@@ -256,11 +276,12 @@ def run_discrete(cfg: azo.Config, model, root_states: np.ndarray, tree_id0: int 
 
         M.MCTS.expansion = staticmethod(expansion)
         try:
-            env = CartPoleEnv(root_states[b])
+            base_env = CartPoleEnv(root_states[b])
+            env = wrap_like_make_game(base_env, modify)
             mcts = M.MCTSDiscrete(model=model, num_actions=A, n_rollouts=cfg.n_rollouts, c_uct=cfg.c_uct,
                                   gamma=_gamma_arg(cfg.gamma), epsilon=cfg.epsilon,
                                   V_target_policy=cfg.V_target_policy, device="cpu",
-                                  root_state=np.array(env.state))
+                                  root_state=np.array(base_env.state))
             mcts.search(env)
             root_n_init = 0
             if second_search:
@@ -276,7 +297,7 @@ def run_discrete(cfg: azo.Config, model, root_states: np.ndarray, tree_id0: int 
                 mcts.root_node._cid = 0
                 mcts.search(env)
             mcts.root_node._cid = 0
-            out["root_state"][b] = env.state
+            out["root_state"][b] = base_env.state
             out["root_n_init"][b] = root_n_init
             out["draws"][b] = rng.draws
             _dump_discrete(mcts, b, out, A)

@@ -25,6 +25,8 @@ def run_engine(cfg: azo.Config, weights, root_state, root_n_init=None, tree_id0=
     try:
         if weights is not None:
             eng.set_weights(weights)
+        if cfg.reward_step != 1.0 or cfg.reward_terminal != 1.0:
+            eng.set_reward_model(cfg.reward_step, cfg.reward_terminal)
         if tapes is not None:
             eng.set_tapes(tapes["V"], tapes.get("prior"), tapes.get("action"))
         if host:

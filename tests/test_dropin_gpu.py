@@ -47,6 +47,48 @@ def test_mcts_discrete_dropin(name, eval_q8):
     mcts.close()
 
 
+class _Wrapper:  # gym.Wrapper stand-in: the drop-in recognises the reference's wrapper classes by name (rl/wrappers.py)
+    def __init__(self, env):
+        self.env = env
+
+
+class ReparametrizeWrapper(_Wrapper):
+    pass
+
+
+class ScaleRewardWrapper(_Wrapper):
+    pass
+
+
+@pytest.mark.parametrize("name, wrap", [("cartpole_n50_wrap_r", lambda e: ReparametrizeWrapper(e)),
+                                        ("cartpole_n50_wrap_s_g099", lambda e: ScaleRewardWrapper(e)),
+                                        ("cartpole_n200_wrap_rs_terminal", lambda e: ScaleRewardWrapper(ReparametrizeWrapper(e)))])
+def test_mcts_discrete_dropin_with_reward_wrappers(name, wrap):
+    """Env wrapped like rl/make_game.py does for the -v0r / -v0s / -v0rs names: the search through the drop-in class equals the
+    unmodified reference's search through its own wrapper classes (golden) and the oracle bit for bit; then the plain env again."""
+    from alphazero_gym_b200.search.mcts import MCTSDiscrete
+    cfg, g = G.load(name)
+    cfg.eval_mode = azo.EVAL_Q8
+    model = _model(cfg, g["weights"])
+    base = CartPoleEnv(g["root_state"][0])
+    mcts = MCTSDiscrete(model=model, num_actions=2, n_rollouts=cfg.n_rollouts, c_uct=cfg.c_uct, gamma=cfg.gamma, epsilon=cfg.epsilon,
+                        V_target_policy=cfg.V_target_policy, device="cuda:0", root_state=np.array(base.state), seed=cfg.seed)
+    mcts.search(Env=wrap(base))
+    _, _, counts, Q, V = mcts.return_results("max_visit")
+    assert np.array_equal(counts, g["counts"][0]) and close(Q, g["Q"][0]) and close(V, g["V_target"][0])
+    cfg.math_mode = azo.MATH_DET
+    ref = azo.search(cfg, g["weights"], g["root_state"][:1])
+    assert np.array_equal(counts, ref["counts"][0]) and np.array_equal(Q, ref["Q"][0]) and V == ref["V_target"][0]
+    # the same object on the plain env: the reward model goes back to 1.0 / 1.0 (second search of the object = tree id 1)
+    mcts.root_node = None
+    mcts.search(Env=base)
+    _, _, counts, Q, V = mcts.return_results("max_visit")
+    cfg.reward_step = cfg.reward_terminal = 1.0
+    ref = azo.search(cfg, g["weights"], g["root_state"][:1], tree_id0=1)
+    assert np.array_equal(counts, ref["counts"][0]) and np.array_equal(Q, ref["Q"][0]) and V == ref["V_target"][0]
+    mcts.close()
+
+
 def test_mcts_discrete_forward_reuses_root_count():
     """forward() keeps only root.n; the next search equals the oracle run with that root_n_init."""
     from alphazero_gym_b200.search.mcts import MCTSDiscrete

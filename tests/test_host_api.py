@@ -155,16 +155,20 @@ def test_hydra_yaml_drop_ins_instantiate():
         assert obj.n_rollouts == cfg["n_rollouts"] and obj.c_uct == cfg["c_uct"] and obj.gamma == cfg["gamma"]
 
 
-def test_wrapped_envs_are_refused_not_silently_unwrapped():
+def test_wrapped_envs_are_carried_or_refused_not_silently_unwrapped():
     """rl/make_game.py:71-83 wraps the env for the -v0n/r/p/s name suffixes (rl/wrappers.py): the search would see other rewards /
-    observations than the engine's plain dynamics produce, so the drop-in refuses them; a plain TimeLimit-style wrapper is unwrapped."""
+    observations than the engine's plain dynamics produce.  The two arithmetic reward wrappers become the engine's reward model,
+    evaluated with the wrappers' own expressions; the others are refused; a plain TimeLimit-style wrapper is unwrapped."""
     import numpy as np
     import pytest
-    from alphazero_gym_b200._cabi import DISCRETE
-    from alphazero_gym_b200.search.mcts import env_hidden_state
+    from alphazero_gym_b200._cabi import CONTINUOUS, DISCRETE
+    from alphazero_gym_b200.search.mcts import env_hidden_state, reward_model
 
     class CartPoleEnv:
         state = np.zeros(4)
+
+    class PendulumEnv:
+        state = np.zeros(2)
 
     class TimeLimit:
         def __init__(self, env):
@@ -173,6 +177,27 @@ def test_wrapped_envs_are_refused_not_silently_unwrapped():
     class ReparametrizeWrapper(TimeLimit):
         pass
 
+    class ScaleRewardWrapper(TimeLimit):
+        pass
+
+    class PILCOWrapper(TimeLimit):
+        pass
+
+    class NormalizeWrapper(TimeLimit):
+        pass
+
     assert env_hidden_state(TimeLimit(CartPoleEnv()), DISCRETE).shape == (4,)
+    assert reward_model(TimeLimit(CartPoleEnv()), DISCRETE) == (1.0, 1.0)
+    assert env_hidden_state(ReparametrizeWrapper(CartPoleEnv()), DISCRETE).shape == (4,)
+    assert reward_model(ReparametrizeWrapper(CartPoleEnv()), DISCRETE) == (0.005, -1.0)
+    assert reward_model(ScaleRewardWrapper(CartPoleEnv()), DISCRETE) == (1.0 / 250.0, 1.0 / 250.0)
+    # prepare_control_env order: Reparametrize inside, ScaleReward outside (rl/make_game.py:75-83)
+    assert reward_model(ScaleRewardWrapper(ReparametrizeWrapper(CartPoleEnv())), DISCRETE) == (0.005 / 250.0, -1 / 250.0)
+    assert reward_model(ReparametrizeWrapper(PendulumEnv()), CONTINUOUS) == (1.0, 1.0)
     with pytest.raises(NotImplementedError):
-        env_hidden_state(ReparametrizeWrapper(CartPoleEnv()), DISCRETE)
+        reward_model(ScaleRewardWrapper(PendulumEnv()), CONTINUOUS)
+    for bad in (PILCOWrapper, NormalizeWrapper):
+        with pytest.raises(NotImplementedError):
+            env_hidden_state(bad(CartPoleEnv()), DISCRETE)
+        with pytest.raises(NotImplementedError):
+            reward_model(ScaleRewardWrapper(bad(CartPoleEnv())), DISCRETE)
