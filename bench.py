@@ -649,7 +649,7 @@ def main():
     extras, strong = {}, None
     if args.workload is None and not args.no_extra:
         for name in EXTRA_WORKLOADS:
-            extras[name] = measure(ctx, args, name, traffic=False)
+            extras[name] = measure(ctx, args, name, traffic=not name.startswith("selfplay"))  # (measure() skips the ncu pass at N > 1)
         if ctx.world > 1 and B % ctx.world == 0:
             # BASELINE config 4 as worded: the SAME 65536 trees sharded B / N per GPU (parallel.shard_range): strong scaling
             strong = measure(ctx, args, head, trees_per_gpu=B // ctx.world, scaling="strong", cpu_baseline=False, traffic=False)
