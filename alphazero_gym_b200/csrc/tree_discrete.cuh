@@ -402,7 +402,7 @@ __device__ __forceinline__ void ds_sts64(uint32_t a, double v) { asm volatile("s
 __device__ __forceinline__ void ds_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void ds_sts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
 
-__device__ __forceinline__ void ds_step(const DsCtx& cx, int i, bool valid, int lane, const bool BACKUP, const bool SELECT) {
+__device__ __forceinline__ void ds_step(const DsCtx& cx, const DsCtx* cxs, int i, bool valid, int lane, const bool BACKUP, const bool SELECT) {
     const uint32_t FULL = 0xFFFFFFFFu;
     DSP_BEGIN();
     const SmTrees sm = cx.sm;
@@ -532,7 +532,9 @@ __device__ __forceinline__ void ds_step(const DsCtx& cx, int i, bool valid, int 
                     const double s[4] = {sp[0], sp[1], sp[2], sp[3]};
                     double o[4], rew;
                     const bool term = env::cartpole_step(s, a, o, rew);
-                    rew = term ? cx.reward_terminal : cx.reward_step;  // rl/wrappers.py (1.0 / 1.0 without wrappers)
+                    // rl/wrappers.py (1.0 / 1.0 without wrappers); read from the shared-memory block here, once per step: as part of the
+                    // register copy the two constants cost 20 M sims/s in spills (profiles/README.md r2x)
+                    rew = term ? cxs->reward_terminal : cxs->reward_step;
                     double* so = cx.dstate + ((size_t)i * R + child) * 4;
                     so[0] = o[0]; so[1] = o[1]; so[2] = o[2]; so[3] = o[3];
                     DRow nr;
@@ -577,7 +579,7 @@ void ds_phase(const DsCtx* cxs, int mode) {
     const int i = tid / cx.lpt, i0 = (tid & ~31) / cx.lpt;  // this lane's tree; the first tree of its warp
     if (i0 >= cx.ntrees) return;  // no tree on this warp
     // lanes without a tree shadow the warp's first tree (they read what its lanes read, at the same points, and write nothing)
-    ds_step(cx, i < cx.ntrees ? i : i0, i < cx.ntrees, lane, (mode & 1) != 0, (mode & 2) != 0);
+    ds_step(cx, cxs, i < cx.ntrees ? i : i0, i < cx.ntrees, lane, (mode & 1) != 0, (mode & 2) != 0);
 }
 
 // end of the search: rows in use and per-tree scalars back to the global tables (cooperatively, `nthreads` threads of the CTA)
