@@ -60,6 +60,15 @@ __device__ __forceinline__ void umma_i8_n64(uint32_t tmem_d, uint32_t da_lo, uin
         "r"(da_lo), "r"(db_lo), "r"(Q2_IDESC), "r"(accumulate), "r"(Q2_DESC_HI)
         : "memory");
 }
+// one lane of a converged warp (elect.sync): the MMA warp runs its loop with all 32 lanes so that descriptors, window addresses and
+// barrier parities are warp-uniform values (uniform registers), and only the tcgen05 instructions themselves sit in the elected branch.
+// With the whole loop under `lane == 0` every UTCIMMA was preceded by ~12 instructions moving its operands from the thread's registers
+// into uniform ones (R2UR + ELECT ...): ~150 instructions per batch of 12 MMAs issued by one thread at lone-warp latency
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -411,7 +420,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
     } else if (warp >= 16) {
         // ---- MMA warpgroup: gives its registers to the epilogue warps; one thread issues, in the order the epilogue warps consume
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (warp == 16 && lane == 0) {
+        if (warp == 16) {
             uint32_t rph = 0, fph = 0;  // bit T: parity of the next wait on ready[T] / freeb[T]
 #pragma unroll 1
             for (int s = 0; s < n_evals; ++s)
@@ -429,6 +438,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
                         const uint32_t aH = q2_desc_lo(smem_u32(sA) + (uint32_t)T * 3 * QMLP_PLANE), aM = aH + 1024, aL = aH + 2048;
                         const uint32_t bH = q2_desc_lo(smem_u32(sB) + (uint32_t)l * 3 * QMLP_PLANE + (uint32_t)h * 1024u), bM = bH + 1024, bL = bH + 2048;
                         const uint32_t acc = tb + T * Q2_ACC_COLS;
+                        if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_i8_n64(acc, aH + k * 256, bH + k * 256, k > 0);        // PA = xh*wh
 #pragma unroll
@@ -442,6 +452,8 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_i8_n64(acc + 128, aL + k * 256, bH + k * 256, 1);      //    + xl*wh
                         umma_commit(&full[T]);
+                        }
+                        __syncwarp();
                     }
                 }
             }

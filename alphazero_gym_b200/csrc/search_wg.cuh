@@ -273,11 +273,13 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
     mbar_wait(&wbar, 0);
 
     if (warp >= 16) {
-        // ---- MMA warpgroup: gives its registers away; lane 0 of warps 16 and 17 issue for slot 0 and slot 1
+        // ---- MMA warpgroup: gives its registers away; warps 16 and 17 issue for slot 0 and slot 1.  The whole warp runs the loop, so
+        // that descriptors and window addresses are warp-uniform (uniform registers), and one elected lane issues the tcgen05
+        // instructions (qmlp2.cuh elect_one: with the loop under `lane == 0` every UTCIMMA carried ~12 instructions of R2UR traffic)
         // (56 registers: with the 24 of qmlp2.cuh the issue loop below spills its descriptors, and a local-memory reload in front of
         // every tcgen05.mma -- this kernel has almost no L1 -- made an MMA cost ~290 cycles instead of ~46, profiles/README.md r2b)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (warp < 18 && lane == 0) {
+        if (warp < 18) {
             const int slot = warp - 16;
             uint32_t rph = 0, aph = 0;  // parity of the next wait on ready[slot]; bit w: on accfree[slot][w]
             const uint32_t aH = q2_desc_lo(smem_u32(sA) + (uint32_t)slot * 3 * QMLP_PLANE), aM = aH + 1024, aL = aH + 2048;
@@ -300,6 +302,7 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
                         // step k; +768 per K step (two k chunks of 6 KB)
                         const uint32_t bq = wg_descb_lo(smem_u32(sB) + (uint32_t)l * 3 * QMLP_PLANE + (uint32_t)k * WG_B_STEP);
                         const uint32_t acc = tb + slot * WG_SLOT_COLS + w * WG_WIN_COLS;
+                        if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk) {
                             umma_i8_wg(acc, aH + kk * 256, bq + kk * 768, WG_IDESC(48), kk > 0);   // PA | PB | PC  = / += xh x [wh | wm | wl]
@@ -307,6 +310,8 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
                             umma_i8_wg(acc + 32, aL + kk * 256, bq + kk * 768, WG_IDESC(16), 1);    //           PC += xl x [wh]
                         }
                         umma_commit(&full[slot][w]);
+                        }
+                        __syncwarp();
                     }
                 }
             }
