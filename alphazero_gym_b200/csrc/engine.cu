@@ -575,7 +575,7 @@ static cudaError_t launch_qmlp_t(const azg_engine* e, const MlpParams& m, cudaSt
         cudaFuncAttributes fa;
         ce = cudaFuncGetAttributes(&fa, k_search_wg<S, ACT, NL>);
         if (ce != cudaSuccess) return ce;
-        if (fa.numRegs * WG_THREADS < WG_EPI_THREADS * 104 + 128 * 56) return cudaErrorLaunchOutOfResources;
+        if (fa.numRegs * WG_THREADS < WG_EPI_THREADS * WG_EPI_REGS + 128 * WG_MMA_REGS) return cudaErrorLaunchOutOfResources;
         return cudaFuncSetAttribute(k_search_wg<S, ACT, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->wg_smem);
     }
     const int grid = std::max(1, std::min((m.n + 127) / 128, e->sm_count));

@@ -56,6 +56,11 @@ __device__ __forceinline__ void umma_i8_wg(uint32_t tmem_d, uint32_t da_lo, uint
 }
 __device__ __forceinline__ uint32_t wg_descb_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (((uint32_t)WG_B_KCHUNK >> 4) << 16); }
 
+#ifndef WG_EPI_REGS
+#define WG_EPI_REGS 104  // registers of a tree + evaluation thread / of an MMA-warpgroup thread after setmaxnreg (granularity 8).  112 / 24
+#define WG_MMA_REGS 56   // measured worse: the issue loop spills at 24 (waiting for MMAs 6.6 % -> 15 %, 1142 -> 1035 M sims/s, r2z)
+#endif
+
 // per-thread view of its slot
 struct WgSlot {
     uint32_t tacc;      // TMEM address (lane quarter of this warp, first column of the slot)
@@ -278,7 +283,7 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
         // instructions (qmlp2.cuh elect_one: with the loop under `lane == 0` every UTCIMMA carried ~12 instructions of R2UR traffic)
         // (56 registers: with the 24 of qmlp2.cuh the issue loop below spills its descriptors, and a local-memory reload in front of
         // every tcgen05.mma -- this kernel has almost no L1 -- made an MMA cost ~290 cycles instead of ~46, profiles/README.md r2b)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WG_MMA_REGS));
         if (warp < 18) {
             const int slot = warp - 16;
             uint32_t rph = 0, aph = 0;  // parity of the next wait on ready[slot]; bit w: on accfree[slot][w]
@@ -318,7 +323,7 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
         }
     } else {
         // ---- tree + evaluation warpgroups
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 512 x 104 + 128 x 56 = 60416 <= 640 x 96, the CTA's pool at launch (engine.cu checks it)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WG_EPI_REGS));  // 512 x 104 + 128 x 56 = 60416 <= 640 x 96, the CTA's pool at launch (engine.cu checks it)
         const int g = warp >> 2, slot = g & 1, half = g >> 1;
         const int r = (warp & 3) * 32 + lane;  // row of the tile = TMEM lane
         WgSlot sl;
