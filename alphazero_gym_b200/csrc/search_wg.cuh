@@ -61,11 +61,31 @@ __device__ __forceinline__ uint32_t wg_descb_lo(uint32_t saddr) { return ((saddr
 #define WG_MMA_REGS 56   // measured worse: the issue loop spills at 24 (waiting for MMAs 6.6 % -> 15 %, 1142 -> 1035 M sims/s, r2z)
 #endif
 
+// mbarrier operations on a shared-memory ADDRESS (qmlp.cuh mbar_wait / qmlp2.cuh mbar_arrive take generic pointers)
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {  // bounded like mbar_wait: a protocol error traps instead of hanging
+    int spins = 0;
+    while (!mbar_try_wait_s(bar, parity, 20000u)) {
+        if (++spins > (1 << 22)) {
+            printf("mbar_wait timeout: block %d thread %d barrier smem 0x%x parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+
 // per-thread view of its slot
 struct WgSlot {
     uint32_t tacc;      // TMEM address (lane quarter of this warp, first column of the slot)
     int8_t* sA;         // [3][QMLP_PLANE] A-operand digit planes of the slot
-    uint64_t *ready, *full, *accfree, *slotfree;  // full / accfree: [2] (one per accumulator window); slotfree: [2] (one per warpgroup of the slot)
+    uint32_t ready, full, accfree, slotfree;  // mbarriers as 32-bit shared addresses (half the registers of generic pointers, and no
+                                              // conversion per use); full / accfree: [2] (one per accumulator window, + 8 bytes);
+                                              // slotfree: [2] (one per warpgroup of the slot)
     uint32_t fullph;  // bit w: parity of the next wait on full[w]
     long long cyc_full;  // cycles spent waiting for MMAs (azg_fused_stats)
 };
@@ -87,7 +107,7 @@ __device__ __forceinline__ float wg_quantise_row(const WgSlot& sl, bool wact, in
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of A -> visible to the tensor core
     }
     tc_fence_before();
-    mbar_arrive(sl.ready);
+    mbar_arrive_s(sl.ready);
     return cx;
 }
 
@@ -137,7 +157,7 @@ __device__ __forceinline__ void wg_evaluate(const MlpParams& p, WgSlot& sl, cons
         for (int k = 0; k < 8; ++k) {
             const int w = k & 1;
             const long long f0 = clock64();
-            mbar_wait(sl.full + w, (sl.fullph >> w) & 1u);
+            mbar_wait_s(sl.full + 8u * w, (sl.fullph >> w) & 1u);
             sl.fullph ^= 1u << w;
             tc_fence_after();
             sl.cyc_full += clock64() - f0;
@@ -149,7 +169,7 @@ __device__ __forceinline__ void wg_evaluate(const MlpParams& p, WgSlot& sl, cons
                 tmem_ld16(ta + 32, pc);
                 tmem_wait_ld();
                 tc_fence_before();
-                if (k < 6) mbar_arrive(sl.accfree + w);  // the window may be overwritten by the MMAs of step k + 2
+                if (k < 6) mbar_arrive_s(sl.accfree + 8u * w);  // the window may be overwritten by the MMAs of step k + 2
                 const float2* cb = cwb + l * 128 + 16 * k;
                 float v[16];
 #pragma unroll
@@ -168,7 +188,7 @@ __device__ __forceinline__ void wg_evaluate(const MlpParams& p, WgSlot& sl, cons
                 tmem_st16f(sl.tacc + WG_STASH_COL + 16 * k, v);
             } else {
                 tc_fence_before();
-                if (k < 6) mbar_arrive(sl.accfree + w);
+                if (k < 6) mbar_arrive_s(sl.accfree + 8u * w);
             }
         }
         if (wact) tmem_wait_st();
@@ -329,7 +349,7 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
         WgSlot sl;
         sl.tacc = tb + ((uint32_t)((warp & 3) * 32) << 16) + slot * WG_SLOT_COLS;
         sl.sA = sA + (size_t)slot * 3 * QMLP_PLANE;
-        sl.ready = &ready[slot]; sl.full = full[slot]; sl.accfree = accfree[slot]; sl.slotfree = slotfree[slot];
+        sl.ready = smem_u32(&ready[slot]); sl.full = smem_u32(full[slot]); sl.accfree = smem_u32(accfree[slot]); sl.slotfree = smem_u32(slotfree[slot]);
         sl.fullph = 0;
         sl.cyc_full = 0;
         bool first_use = true;
@@ -363,7 +383,7 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
             // and waits on the other's, so every thread waits for consecutive phases of a barrier (a parity wait tells only two
             // consecutive phases apart: one barrier for both warpgroups lets a fast thread slip a whole use ahead)
             if (half == 1 || !first_use) {
-                mbar_wait(sl.slotfree + (half ^ 1), useph);
+                mbar_wait_s(sl.slotfree + 8u * (half ^ 1), useph);
                 useph ^= 1u;
             }
             first_use = false;
@@ -373,7 +393,7 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
 #pragma unroll
             for (int i = 0; i < Q2_MAX_PO; ++i) out[i] = 0.0f;
             if (tvalid) wg_evaluate<S, ACT, NL>(p, sl, fl, wact, valid, gr, r, out);
-            mbar_arrive(sl.slotfree + half);  // TMEM and the A buffer of the slot are free again
+            mbar_arrive_s(sl.slotfree + 8u * half);  // TMEM and the A buffer of the slot are free again
             const long long c2 = clock64();
             // ---- finish the row, then the tree step of this thread's tree
             if (valid) {
