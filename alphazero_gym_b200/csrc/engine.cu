@@ -1088,6 +1088,10 @@ extern "C" int azg_fused_stats(azg_engine* e, int64_t out[8]) {
             "discrete level loop: scores %llu draw+pick %llu next row %llu over %llu warp-levels\n", h[8], h[9], h[10], h[11], h[12], h[0], h[4], h[13], h[14], h[11], h[15]);
 #endif
 #ifdef AZG_EVAL_PROF
+    if (e->last_fused_kind == 2)
+        fprintf(stderr, "k_search_wg, cycles per warpgroup and search spent waiting for MMAs: at column step 0 of a layer %llu | step 1 %llu | steps 2..7 %llu | kernel %llu\n",
+                h[8] / (h[4] ? h[4] : 1), h[9] / (h[4] ? h[4] : 1), h[10] / (h[4] ? h[4] : 1), h[0] / (h[4] ? h[4] : 1));
+    else
     fprintf(stderr, "evaluation timeline of epilogue thread 0, cycles per CTA and search: layer 0 %llu | MMA wait %llu | load + convert %llu | stash / quantise / heads %llu | "
             "post-processing wait %llu | tree phase %llu | kernel %llu\n", h[8] / (h[4] ? h[4] : 1), h[9] / (h[4] ? h[4] : 1), h[10] / (h[4] ? h[4] : 1), h[11] / (h[4] ? h[4] : 1),
             h[12] / (h[4] ? h[4] : 1), h[13] / (h[4] ? h[4] : 1), h[0] / (h[4] ? h[4] : 1));

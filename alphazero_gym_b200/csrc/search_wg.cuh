@@ -88,6 +88,9 @@ struct WgSlot {
                                               // slotfree: [2] (one per warpgroup of the slot)
     uint32_t fullph;  // bit w: parity of the next wait on full[w]
     long long cyc_full;  // cycles spent waiting for MMAs (azg_fused_stats)
+#ifdef AZG_EVAL_PROF
+    long long cyc_k[3];  // ... of which at column step 0, step 1, steps 2..7
+#endif
 };
 
 // scale of a row from its maximum, then the row's 128 stashed activations -> three digit planes in shared memory -> "ready"
@@ -161,6 +164,9 @@ __device__ __forceinline__ void wg_evaluate(const MlpParams& p, WgSlot& sl, cons
             sl.fullph ^= 1u << w;
             tc_fence_after();
             sl.cyc_full += clock64() - f0;
+#ifdef AZG_EVAL_PROF
+            sl.cyc_k[k < 2 ? k : 2] += clock64() - f0;
+#endif
             if (wact) {
                 const uint32_t ta = sl.tacc + w * WG_WIN_COLS;
                 int32_t pa[16], pb[16], pc[16];
@@ -352,6 +358,9 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
         sl.ready = smem_u32(&ready[slot]); sl.full = smem_u32(full[slot]); sl.accfree = smem_u32(accfree[slot]); sl.slotfree = smem_u32(slotfree[slot]);
         sl.fullph = 0;
         sl.cyc_full = 0;
+#ifdef AZG_EVAL_PROF
+        sl.cyc_k[0] = sl.cyc_k[1] = sl.cyc_k[2] = 0;
+#endif
         bool first_use = true;
         uint32_t useph = 0;  // parity of the next wait on the other warpgroup's release barrier
         const Tabs tabs = {s_pw, s_rcp, s_sq, FUSED_TAB};
@@ -428,6 +437,9 @@ k_search_wg(const MlpParams p, const TreeParams tp, const int n_sims, const int 
             atomicAdd(p.stats + 1, (unsigned long long)cyc_tree);
             atomicAdd(p.stats + 2, (unsigned long long)cyc_slot);
             atomicAdd(p.stats + 3, (unsigned long long)sl.cyc_full);
+#ifdef AZG_EVAL_PROF
+            for (int k = 0; k < 3; ++k) atomicAdd(p.stats + 8 + k, (unsigned long long)sl.cyc_k[k]);
+#endif
             atomicAdd(p.stats + 4, 1ull);
         }
     }
