@@ -16,9 +16,9 @@ pytestmark = pytest.mark.gpu
 TSM = "two_phase_trees_in_shared_memory"
 
 
-def _weights():
+def _weights(cfg=None):
     from alphazero_gym_b200.network import init_policy_weights
-    return init_policy_weights(34, 4, 128, 2, 2)
+    return init_policy_weights(34, 4, 128, cfg.n_hidden if cfg is not None else 2, 2)
 
 
 def _roots(B, seed=34):
@@ -36,7 +36,8 @@ def _run(cfg, roots, root_n_init=None, tree_id0=0, no_tsm=False):
     try:
         eng = SearchEngine(E.engine_config(cfg, B))
         try:
-            eng.set_weights(_weights())
+            eng.set_weights(_weights(cfg))
+            eng.set_reward_model(cfg.reward_step, cfg.reward_terminal)
             rn = None if root_n_init is None else torch.from_numpy(np.ascontiguousarray(root_n_init, np.int32)).cuda()
             eng.search(torch.from_numpy(np.ascontiguousarray(roots, np.float64)).cuda(), cfg.n_rollouts, rn, tree_id0)
             eng.status()
@@ -72,6 +73,8 @@ CASES = {
     "two_waves_6000": (6000, dict(n_rollouts=50, epsilon=0.1), False),          # two launches of 3000 trees
     "deep_300x200": (300, dict(n_rollouts=200, epsilon=0.05), False),           # paths > 8 levels, > 16 levels per search step
     "eps0_on_policy_reuse": (257, dict(n_rollouts=64, epsilon=0.0, gamma=0.99, V_target_policy="on_policy"), True),
+    "three_layers_elu": (300, dict(n_rollouts=30, epsilon=0.1, n_hidden=3, activation=azo.ACT_ELU), False),  # two tensor-core layers per evaluation
+    "reward_wrappers_rs": (300, dict(n_rollouts=60, epsilon=0.1, reward_step=0.005 / 250.0, reward_terminal=-1 / 250.0), False),
 }
 
 
@@ -83,7 +86,7 @@ def test_shared_memory_trees_equal_oracle_and_hbm_rows(name):
     roots = _roots(B)
     rn = np.random.default_rng(5).integers(0, 30, B).astype(np.int32) if reuse else None
     tree_id0 = 1000 if reuse else 0
-    ref = azo.search(cfg, _weights(), roots, rn, tree_id0=tree_id0, n_threads=os.cpu_count() or 8)
+    ref = azo.search(cfg, _weights(cfg), roots, rn, tree_id0=tree_id0, n_threads=os.cpu_count() or 8)
     out = _fit(_run(cfg, roots, rn, tree_id0), ref)
     assert out["kernel"] == TSM, out["kernel"]
     assert out["launches"] == (2 if name.startswith("two_waves") else 1)
