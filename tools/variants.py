@@ -31,11 +31,11 @@ def build(specs):
         log, _ = p.communicate()
         with open(out + ".log", "w") as f:
             f.write(log)
-        spill = [l.strip() for l in log.splitlines() if "k_qmlp2ILi3ELi1ELi2ELb1" in l or "k_qmlp2ILi4ELi0ELi1ELb1" in l]
         info = []
         lines = log.splitlines()
         for i, l in enumerate(lines):
-            if "Compiling entry function '_Z7k_qmlp2ILi3ELi1ELi2ELb1E" in l or "Compiling entry function '_Z7k_qmlp2ILi4ELi0ELi1ELb1E" in l:
+            if any(k in l for k in ("Compiling entry function '_Z7k_qmlp2ILi3ELi1ELi2ELb1ELb0E", "Compiling entry function '_Z7k_qmlp2ILi4ELi0ELi1ELb1ELb1E",
+                                    "Compiling entry function '_Z11k_search_wgILi3ELi1ELi2E")):
                 info.append(" | ".join(x.strip().replace("ptxas info    : ", "") for x in lines[i + 1:i + 4]))
         print(name, "rc", p.returncode, *info, sep="\n   ")
 
