@@ -593,7 +593,7 @@ static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const
         // rows in HBM, whose simulation takes 32 us whatever the batch (measured, profiles/README.md r2p: 8192 trees 248 M sims/s
         // there against 2 x 4096 at 337 M) -- so such a batch is cut into equal chunks, one launch each
         int cap = 0;
-        while (cap < 128 && qmlp2_tsm_smem_bytes(NL, e->qfl_count, cap + 1, p.R) <= e->tsm_smem_max) ++cap;
+        while (cap < 128 && qmlp2_tsm_smem_bytes(NL, e->qfl_count, cap + 1, p.R, e->PO_PAD) <= e->tsm_smem_max) ++cap;
         const long long wave = (long long)cap * e->sm_count;
         if (cap > 0 && !p.rng_mt && !getenv("AZG_NO_TSM") && e->fused_mode != 2 && p.B > wave && p.B <= 2 * wave) chunk = (p.B + 1) / 2;
     }
@@ -613,14 +613,14 @@ static cudaError_t launch_fused_t(const azg_engine* e, const MlpParams& m, const
         if constexpr (S == 4) {
             const int per = (hi - lo + e->sm_count - 1) / e->sm_count;
             if (two_phase && !p.rng_mt && !getenv("AZG_NO_TSM") && per <= 128 &&
-                qmlp2_tsm_smem_bytes(NL, e->qfl_count, per, p.R) <= e->tsm_smem_max)
+                qmlp2_tsm_smem_bytes(NL, e->qfl_count, per, p.R, e->PO_PAD) <= e->tsm_smem_max)
                 tsm_per = per;
         }
         const_cast<azg_engine*>(e)->last_fused_kind = tsm_per ? 3 : (two_phase ? 1 : 2);
         if (tsm_per) {
             if constexpr (S == 4) {
                 const int grid = (hi - lo + tsm_per - 1) / tsm_per;
-                ce = launch_ex(e, k_qmlp2<S, ACT, NL, true, true>, grid, Q2_THREADS, qmlp2_tsm_smem_bytes(NL, e->qfl_count, tsm_per, p.R), st, m, p, N, lo, hi);
+                ce = launch_ex(e, k_qmlp2<S, ACT, NL, true, true>, grid, Q2_THREADS, qmlp2_tsm_smem_bytes(NL, e->qfl_count, tsm_per, p.R, e->PO_PAD), st, m, p, N, lo, hi);
             }
         } else if (two_phase) {
             const int grid = std::max(1, std::min((hi - lo + 127) / 128, e->sm_count));

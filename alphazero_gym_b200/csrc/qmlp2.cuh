@@ -42,9 +42,9 @@ __host__ __device__ inline size_t qmlp2_smem_bytes(int NL, int qfl_count, bool f
 }
 // TSM (trees in shared memory, tree_discrete.cuh ds_step): one tile per CTA, so ONE A-operand slot; behind the tables the rows,
 // per-tree scalars, network inputs and leaf words of the CTA's trees
-#define Q2_TSM_PER_TREE(R) ((size_t)(R) * (sizeof(DRow) + 2) + sizeof(STree) + sizeof(float4) + sizeof(int32_t))
-__host__ __device__ inline size_t qmlp2_tsm_smem_bytes(int NL, int qfl_count, int trees, int R) {
-    return qmlp2_smem_bytes(NL, qfl_count, true) - 3 * QMLP_PLANE + 64 + (size_t)trees * Q2_TSM_PER_TREE(R);
+#define Q2_TSM_PER_TREE(R, PO_PAD) ((size_t)(R) * (sizeof(DRow) + 2) + sizeof(STree) + sizeof(float4) + sizeof(int32_t) + 4 * (PO_PAD) * sizeof(float))
+__host__ __device__ inline size_t qmlp2_tsm_smem_bytes(int NL, int qfl_count, int trees, int R, int po_pad) {
+    return qmlp2_smem_bytes(NL, qfl_count, true) - 3 * QMLP_PLANE + 64 + 16 + (size_t)trees * Q2_TSM_PER_TREE(R, po_pad);
 }
 // row of the digit planes that holds output j: half h = (j/16)%2, D column of the half = 16*(j/32) + j%16
 __host__ __device__ inline int qmlp_perm_row(int j) { return 64 * ((j >> 4) & 1) + 16 * (j >> 5) + (j & 15); }
@@ -215,6 +215,27 @@ __device__ __forceinline__ void q2_heads(const Q2Ctx& c, const MlpParams& p, int
     mbar_arrive(c.hfull + T);
 }
 
+// TSM: the same chains, partial sums into shared memory ([4 quarters][PO_PAD][trees]); the tree phase sums them and finishes the row
+__device__ __forceinline__ void q2_heads_tsm(const Q2Ctx& c, const MlpParams& p, bool active, const float* a0, const float* a1, float* part, int ntrees) {
+    if (active) {
+#pragma unroll 1
+        for (int c4 = 0; c4 < p.PO_PAD / 4; ++c4) {
+            float2 lo = make_float2(0.0f, 0.0f), hi = make_float2(0.0f, 0.0f);
+            const float* wp = c.Wh + (c.cq * 32) * p.PO_PAD + c4 * 4;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wp + i * p.PO_PAD);
+                const float ai = i < 16 ? a0[i & 15] : a1[i & 15];
+                const float2 av = make_float2(ai, ai);
+                lo = __ffma2_rn(av, make_float2(w4.x, w4.y), lo);
+                hi = __ffma2_rn(av, make_float2(w4.z, w4.w), hi);
+            }
+            float* d = part + (size_t)(c.cq * p.PO_PAD + c4 * 4) * ntrees + c.r;
+            d[0] = lo.x; d[ntrees] = lo.y; d[2 * ntrees] = hi.x; d[3 * ntrees] = hi.y;
+        }
+    }
+}
+
 // post-processing warp of row group lg: one thread per row of the tile in slot T
 __device__ __forceinline__ void q2_finish_tile(const MlpParams& p, uint32_t tb, const float* bh, int lg, int T, bool need, int gr, int leafw,
                                                double lr, uint64_t* hfree, uint32_t& nev, int& ev_row) {
@@ -303,6 +324,9 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
         smt.X = reinterpret_cast<float4*>(smt.st + (TSM ? nrows : 0));
         smt.leaf = reinterpret_cast<int32_t*>(smt.X + (TSM ? nrows : 0));
         smt.path = reinterpret_cast<uint16_t*>(smt.leaf + (TSM ? nrows : 0));
+        uint8_t* pbase = reinterpret_cast<uint8_t*>(smt.path + (size_t)(TSM ? nrows : 0) * tp.R);
+        pbase += (16u - (smem_u32(pbase) & 15u)) & 15u;
+        smt.part = reinterpret_cast<float*>(pbase);
     }
     MlpParams p_tsm;
     if (TSM) {
@@ -328,10 +352,11 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
         // lpt = 8 (7 warps) 337, lpt = 4 (4 warps) 318 M sims/s -- fewer warps issue fewer instructions in total (both halves of
         // a warp share one stream), more lanes per tree shorten the backup and the draw generation
         cx.lpt = nrows <= 64 ? 8 : 4;
+        cx.po_pad = p_in.PO_PAD;
+        cx.bh = fl + S * 128 + 128 + NL * 2 * 128 + 128 * p_in.PO_PAD;
 #ifdef AZG_TSM_LPT
         cx.lpt = AZG_TSM_LPT;
 #endif
-        cx.pad = 0;
         cx.prof = s_dsprof;
         for (int k = 0; k < 8; ++k) s_dsprof[k] = 0;
         s_dsctx = cx;
@@ -387,7 +412,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
 #pragma unroll 1
         for (int s = 0; s < n_evals; ++s) {
 #pragma unroll 1
-        for (int t = 0; t < ntiles; ++t) {
+        for (int t = 0; t < (TSM ? 0 : ntiles); ++t) {  // TSM: the tree phase finishes the rows itself (tree_discrete.cuh ds_step)
             const int T = t & 1;
             const int row0 = row_begin + t * th;
             const int nv = max(0, min(th, row_end - row0));
@@ -561,7 +586,7 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
                 }
                 EP_STAMP(2);
                 if (h == 0) {
-                    if (l == 0 && (t0 > 0 || s > 0)) {  // the slot's scratch still holds the head partial sums of its previous tile
+                    if (!TSM && l == 0 && (t0 > 0 || s > 0)) {  // the slot's scratch still holds the head partial sums of its previous tile
                         mbar_wait(hfree + T, (hfph >> T) & 1u);
                         hfph ^= 1u << T;
                         tc_fence_after();
@@ -581,6 +606,8 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
                     if (l + 1 < NL) {
                         const float ncx = q2_quantise_store(c, T, wact, u, v, pm);
                         if (T) cx1 = ncx; else cx0 = ncx;
+                    } else if (TSM) {
+                        q2_heads_tsm(c, p, wact && c.r < nrows, u, v, smt.part, nrows);
                     } else {
                         q2_heads(c, p, T, wact, u, v);
                     }

@@ -257,6 +257,7 @@ struct SmTrees {
     float4* X;       // [trees]  network input of the leaf
     int32_t* leaf;   // [trees]  LEAF_* word
     uint16_t* path;  // [trees][R]  recorded path of the current simulation
+    float* part;     // [4][PO_PAD][trees]  head partial sums of the column quarters (qmlp2.cuh q2_heads_tsm): the tree phase finishes the rows
 };
 // Everything the tree phase needs, written once per launch into shared memory by the kernel and copied into registers when the
 // phase starts: with the kernel's own parameter blocks (and ~70 registers of the epilogue live across the phase) the compiler
@@ -271,7 +272,8 @@ struct __align__(16) DsCtx {
     double reward_step, reward_terminal;
     uint32_t k0, k1;     // Philox key
     int64_t tree0;       // global id of the CTA's tree 0
-    int32_t tabn, R, puct_f32, ntrees, lpt, pad;
+    int32_t tabn, R, puct_f32, ntrees, lpt, po_pad;
+    const float* bh; // head biases (shared memory)
     unsigned long long* prof;  // AZG_TREE_PROF builds: per-section cycles of warp 0 (shared memory, no atomics)
 };
 
@@ -411,6 +413,31 @@ __device__ __forceinline__ void ds_step(const DsCtx& cx, const DsCtx* cxs, int i
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);                          // row k of this tree at rows_s + 64 k
     const uint32_t path_s = (uint32_t)__cvta_generic_to_shared(sm.path + (size_t)i * R);       // (row << 1 | action) of level k at path_s + 2 k
     const int gl = lane & (lpt - 1), gbase = lane - gl;
+    if (valid && gl == 0) {
+        // finish the evaluated row (what the post-processing warp does in the other schedules, mlp.cuh mlp_finish_row): sum the head's
+        // four quarter chains in the contract's order, softmax over the two logits, V and priors into the leaf's row.  Done here the
+        // evaluation -> post-processing warp -> tree phase hand-over (an mbarrier round trip and a warp wake-up per simulation) is gone.
+        const int leafw = sm.leaf[i];
+        if (leafw & LEAF_EVAL) {
+            const int nt = cxs->ntrees, pp = cxs->po_pad;
+            const float* part = sm.part + i;
+            const float* bh = cxs->bh;
+            float out[3];
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                const float q0 = part[(0 * pp + o) * nt], q1 = part[(1 * pp + o) * nt], q2 = part[(2 * pp + o) * nt], q3 = part[(3 * pp + o) * nt];
+                out[o] = __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)), bh[o]);
+            }
+            const float m = out[2] > out[1] ? out[2] : out[1];  // softmax_seq over two logits (policies.py:275-297)
+            const float e0 = det::expf_(__fsub_rn(out[1], m)), e1 = det::expf_(__fsub_rn(out[2], m));
+            const float sum = __fadd_rn(__fadd_rn(0.0f, e0), e1);
+            const uint32_t lrow_s = rows_s + 64u * (uint32_t)(leafw & LEAF_ROW_MASK);
+            ds_sts32(lrow_s + 40u, __float_as_uint((leafw & LEAF_TERMINAL) ? 0.0f : out[0]));  // mcts.py:406-410
+            ds_sts32(lrow_s + 32u, __float_as_uint(__fdiv_rn(e0, sum)));
+            ds_sts32(lrow_s + 36u, __float_as_uint(__fdiv_rn(e1, sum)));
+        }
+    }
+    __syncwarp();
     {
         // R = leaf.V; up the path: R = node.r + gamma*R; edge.n += 1; edge.W += R; parent.n += 1 (mcts.py:241-267); then the selection
         // rule of every node whose statistics changed, and of the leaf (whose V and priors the evaluation has just written)
@@ -604,6 +631,7 @@ __device__ __forceinline__ void ds_writeback(const TreeParams& p, const SmTrees&
         p.ctr[t] = st.levels;
         p.ctr[(size_t)p.B + t] = st.levels * 2;
         p.ctr[(size_t)2 * p.B + t] = st.terms;
+        p.ctr[(size_t)3 * p.B + t] = (uint32_t)st.n_rows;  // evaluations: the root and every node created
     }
 }
 
