@@ -313,8 +313,10 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
     const int nrows = row_end - row_begin;
     int ntiles = (nrows + 127) / 128;
     if (ntiles > 1) ntiles = (ntiles + 1) & ~1;
-    // TSM: shared-memory tables of the CTA's trees behind the lookup tables; the evaluation reads its inputs (X, leaf words) from and
-    // writes V / priors into them through a patched copy of the parameter block (generic addresses that point into shared memory)
+    // TSM: shared-memory tables of the CTA's trees behind the lookup tables.  The evaluation reads its network inputs from them through a
+    // patched copy of the parameter block (a generic address that points into shared memory) and leaves the head's partial sums in
+    // `part`; the tree phase finishes the rows itself (tree_discrete.cuh ds_step), so the post-processing warps only keep the phase
+    // barriers' count
     SmTrees smt;
     {
         uint8_t* tbase = reinterpret_cast<uint8_t*>(s_pw + FUSED_TAB + 1);
@@ -332,8 +334,6 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
     if (TSM) {
         p_tsm = p_in;
         p_tsm.X = reinterpret_cast<const float*>(smt.X) - (ptrdiff_t)row_begin * 4;
-        p_tsm.leaf = smt.leaf - row_begin;
-        p_tsm.drows = smt.rows - (ptrdiff_t)row_begin * tp.R;
     }
     const MlpParams& p = TSM ? p_tsm : p_in;
     if (TSM && tid == 0) {
