@@ -413,28 +413,26 @@ __device__ __forceinline__ void ds_step(const DsCtx& cx, const DsCtx* cxs, int i
     const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);                          // row k of this tree at rows_s + 64 k
     const uint32_t path_s = (uint32_t)__cvta_generic_to_shared(sm.path + (size_t)i * R);       // (row << 1 | action) of level k at path_s + 2 k
     const int gl = lane & (lpt - 1), gbase = lane - gl;
-    if (valid && gl == 0) {
+    {
         // finish the evaluated row (what the post-processing warp does in the other schedules, mlp.cuh mlp_finish_row): sum the head's
         // four quarter chains in the contract's order, softmax over the two logits, V and priors into the leaf's row.  Done here the
         // evaluation -> post-processing warp -> tree phase hand-over (an mbarrier round trip and a warp wake-up per simulation) is gone.
+        // Lanes 0, 1, 2 of the group take V and the two logits (one exponential and one division each instead of two in a row).
         const int leafw = sm.leaf[i];
-        if (leafw & LEAF_EVAL) {
-            const int nt = cxs->ntrees, pp = cxs->po_pad;
-            const float* part = sm.part + i;
-            const float* bh = cxs->bh;
-            float out[3];
-#pragma unroll
-            for (int o = 0; o < 3; ++o) {
-                const float q0 = part[(0 * pp + o) * nt], q1 = part[(1 * pp + o) * nt], q2 = part[(2 * pp + o) * nt], q3 = part[(3 * pp + o) * nt];
-                out[o] = __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)), bh[o]);
-            }
-            const float m = out[2] > out[1] ? out[2] : out[1];  // softmax_seq over two logits (policies.py:275-297)
-            const float e0 = det::expf_(__fsub_rn(out[1], m)), e1 = det::expf_(__fsub_rn(out[2], m));
-            const float sum = __fadd_rn(__fadd_rn(0.0f, e0), e1);
+        const int o = gl < 3 ? gl : 2;
+        const int nt = cxs->ntrees, pp = cxs->po_pad;
+        const float* part = sm.part + i;
+        const float q0 = part[(0 * pp + o) * nt], q1 = part[(1 * pp + o) * nt], q2 = part[(2 * pp + o) * nt], q3 = part[(3 * pp + o) * nt];
+        const float out = __fadd_rn(__fadd_rn(__fadd_rn(q0, q1), __fadd_rn(q2, q3)), cxs->bh[o]);
+        const float l0 = __shfl_sync(FULL, out, gbase + 1), l1 = __shfl_sync(FULL, out, gbase + 2);
+        const float m = l1 > l0 ? l1 : l0;  // softmax_seq over two logits (policies.py:275-297)
+        const float e = det::expf_(__fsub_rn(out, m));
+        const float e0 = __shfl_sync(FULL, e, gbase + 1), e1 = __shfl_sync(FULL, e, gbase + 2);
+        const float sum = __fadd_rn(__fadd_rn(0.0f, e0), e1);
+        if (valid && (leafw & LEAF_EVAL) && gl < 3) {
             const uint32_t lrow_s = rows_s + 64u * (uint32_t)(leafw & LEAF_ROW_MASK);
-            ds_sts32(lrow_s + 40u, __float_as_uint((leafw & LEAF_TERMINAL) ? 0.0f : out[0]));  // mcts.py:406-410
-            ds_sts32(lrow_s + 32u, __float_as_uint(__fdiv_rn(e0, sum)));
-            ds_sts32(lrow_s + 36u, __float_as_uint(__fdiv_rn(e1, sum)));
+            if (gl == 0) ds_sts32(lrow_s + 40u, __float_as_uint((leafw & LEAF_TERMINAL) ? 0.0f : out));  // mcts.py:406-410
+            else ds_sts32(lrow_s + 28u + 4u * gl, __float_as_uint(__fdiv_rn(e, sum)));                   // prior[gl - 1]
         }
     }
     __syncwarp();
