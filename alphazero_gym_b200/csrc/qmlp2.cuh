@@ -267,6 +267,137 @@ __device__ __forceinline__ void q2_finish_tile(const MlpParams& p, uint32_t tb, 
     }
 }
 
+// ---- evaluation of ONE thin tile (at most 32 rows) by all 16 epilogue warps: "replicated rows" (whole-search kernel, TSM) -------------
+// A tile of 28 rows fills one TMEM lane group, and a lane group is readable by the warps with warp % 4 == group only -- the four warps
+// of ONE scheduler (evaluation timeline, profiles/README.md r2s: 3040 cycles for layer 0 + quantisation, 1900 for the accumulator
+// conversion, 1800 for quantise / heads per simulation on that scheduler, three schedulers idle).  Here row r of the tile is written
+// into the A operand FOUR times, at rows r, 32 + r, 64 + r, 96 + r, so every lane group holds every tree after the M = 128 MMAs (which
+// cost the same whatever the rows hold), and the 16 threads (lane group lg, column quarter cq) of a tree split its columns: thread
+// (lg, cq) owns the outputs j = 32 cq + 16 h + 4 lg + i (half h < 2, i < 4), a quarter of what thread (cq) owns in the ordinary
+// schedule.  Per-element arithmetic is unchanged; the row maximum is exchanged through shared memory by all 16 warps; the heads keep
+// the contract's summation order (four chains over 32 consecutive activations): the last layer's activations go through shared memory
+// (they alias the A operand, dead by then) and the chain of quarter q runs on warp q -- a different scheduler each --, its partial
+// sums go where the tree phase expects them (SmTrees::part).
+__device__ __forceinline__ void tmem_ld4i(uint32_t taddr, int32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+#define Q2_REP_BAR 5  // named barrier of the 16 epilogue warps (ids 1..4 are the row groups')
+// row maximum over the tree's 16 threads -> scale -> digits of this thread's 8 activations into the four row replicas -> "ready"
+__device__ __forceinline__ float q2_rep_quantise_store(const Q2Ctx& c, const float* a, float pm, int r) {
+    float* pmx = c.pmax;  // [16][32]
+    pmx[(c.lg * 4 + c.cq) * 32 + r] = pm;
+    group_sync(Q2_REP_BAR, Q2_EPI_THREADS);
+    float m = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) m = fmaxf(m, pmx[w * 32 + r]);
+    const int e = q8_exponent(m);
+    const float sx = __uint_as_float((uint32_t)(276 - e) << 23);  // 2^(149-e)
+    const float cx = __uint_as_float((uint32_t)(e - 22) << 23);   // 2^(e-149)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) t[i] = (q8_quant(__fmul_rn(a[4 * h + i], sx)) + 0x8080u) ^ 0x8080u;
+        const uint32_t lo01 = __byte_perm(t[0], t[1], 0x5140), lo23 = __byte_perm(t[2], t[3], 0x5140);
+        const uint32_t hi01 = __byte_perm(t[0], t[1], 0x0062), hi23 = __byte_perm(t[2], t[3], 0x0062);
+        const uint32_t wlo = __byte_perm(lo01, lo23, 0x5410), wmid = __byte_perm(lo01, lo23, 0x7632), whi = __byte_perm(hi01, hi23, 0x5410);
+        int8_t* d = c.sA + (2 * c.cq + h) * 2048 + r * 16 + 4 * c.lg;  // k-chunk (32 cq + 16 h) / 16, bytes 4 lg .. 4 lg + 3 of the row's 16
+#pragma unroll
+        for (int m4 = 0; m4 < 4; ++m4) {
+            *reinterpret_cast<uint32_t*>(d + m4 * 512) = whi;
+            *reinterpret_cast<uint32_t*>(d + m4 * 512 + QMLP_PLANE) = wmid;
+            *reinterpret_cast<uint32_t*>(d + m4 * 512 + 2 * QMLP_PLANE) = wlo;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of A -> visible to the tensor core
+    mbar_arrive(c.ready);
+    return cx;
+}
+// one evaluation of the tile in slot 0 (rows row0 .. row0 + nv - 1, nv <= 32); sact: [128][32] activations of the last layer (aliases the
+// A operand); part: [4][PO_PAD][nv] head partial sums for the tree phase
+template <int S, int ACT, int NL>
+__device__ __forceinline__ void q2_eval_rep(const Q2Ctx& c, const MlpParams& p, int nv, int row0, int lane, uint32_t& fullph, float* sact, float* part) {
+    const int r = lane;
+    const int jb = 32 * c.cq + 4 * c.lg;  // outputs jb + 16 h + i
+    float a[8];
+    float pm = 0.0f;
+    {
+        float x[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) x[s] = 0.0f;
+        if (r < nv) {
+            const float4 v = *reinterpret_cast<const float4*>(p.X + (size_t)(row0 + r) * 4);  // xstride 4 in the whole-search kernel
+            x[0] = v.x; x[1] = v.y; x[2] = v.z;
+            if (S > 3) x[S - 1] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const int j = jb + 16 * (k >> 2) + (k & 3);
+            float2 acc = *reinterpret_cast<const float2*>(c.b0 + j);
+#pragma unroll
+            for (int s = 0; s < S; ++s) acc = __ffma2_rn(make_float2(x[s], x[s]), *reinterpret_cast<const float2*>(c.W0 + s * 128 + j), acc);
+            const float2 e = mlp_act2<ACT>(acc);
+            a[k] = e.x; a[k + 1] = e.y;
+            pm = fmaxf(pm, fmaxf(fabsf(e.x), fabsf(e.y)));
+        }
+    }
+    float cx = q2_rep_quantise_store(c, a, pm, r);
+    const uint32_t ta = c.tb + ((uint32_t)(c.lg * 32) << 16) + 16 * c.cq + 4 * c.lg;
+#pragma unroll 1
+    for (int l = 0; l < NL; ++l) {
+        pm = 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            mbar_wait(c.full, fullph & 1u);
+            fullph ^= 1u;
+            tc_fence_after();
+            int32_t pa[4], pb[4], pc[4];
+            tmem_ld4i(ta, pa);
+            tmem_ld4i(ta + 64, pb);
+            tmem_ld4i(ta + 128, pc);
+            tmem_wait_ld();
+            tc_fence_before();
+            if (h == 0) mbar_arrive(c.freeb);  // the window may be overwritten by the MMAs of half 1
+            const float2* cb = c.cwb + l * 128 + jb + 16 * h;
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {
+                const float4 sb = *reinterpret_cast<const float4*>(cb + i);  // (cw, bias) of outputs i, i+1
+                float u0 = __int2float_rn(pa[i] * 256 + pb[i]);                 // = fma(PA, 256, PB), see the ordinary schedule below
+                float u1 = __int2float_rn(pa[i + 1] * 256 + pb[i + 1]);
+                u0 = __fmaf_rn(u0, 256.0f, q8_i2f_23(pc[i]));
+                u1 = __fmaf_rn(u1, 256.0f, q8_i2f_23(pc[i + 1]));
+                const float2 y = make_float2(__fmaf_rn(u0, __fmul_rn(cx, sb.x), sb.y), __fmaf_rn(u1, __fmul_rn(cx, sb.z), sb.w));
+                const float2 ev = mlp_act2<ACT>(y);
+                a[4 * h + i] = ev.x; a[4 * h + i + 1] = ev.y;
+                pm = fmaxf(pm, fmaxf(fabsf(ev.x), fabsf(ev.y)));
+            }
+        }
+        if (l + 1 < NL) cx = q2_rep_quantise_store(c, a, pm, r);
+    }
+    // heads: the activations of the last layer through shared memory, the chain of quarter q on warp q
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sact[(jb + 16 * (k >> 2) + (k & 3)) * 32 + r] = a[k];
+    group_sync(Q2_REP_BAR, Q2_EPI_THREADS);
+    if (c.cq == 0 && r < nv) {
+        const int q = c.lg;
+#pragma unroll 1
+        for (int c4 = 0; c4 < p.PO_PAD / 4; ++c4) {
+            float2 lo = make_float2(0.0f, 0.0f), hi = make_float2(0.0f, 0.0f);
+            const float* wp = c.Wh + (q * 32) * p.PO_PAD + c4 * 4;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wp + i * p.PO_PAD);
+                const float ai = sact[(q * 32 + i) * 32 + r];
+                const float2 av = make_float2(ai, ai);
+                lo = __ffma2_rn(av, make_float2(w4.x, w4.y), lo);
+                hi = __ffma2_rn(av, make_float2(w4.z, w4.w), hi);
+            }
+            float* d = part + (size_t)(q * p.PO_PAD + c4 * 4) * nv + r;
+            d[0] = lo.x; d[nv] = lo.y; d[2 * nv] = hi.x; d[3 * nv] = hi.y;
+        }
+    }
+}
+
 // FUSED = false: one leaf evaluation of p.n rows (one launch per simulation, engine.cu enqueue_search).
 // FUSED = true: the WHOLE SEARCH of the continuous tree for the trees [chunk_begin, chunk_end) in one persistent launch.
 //   Trees never interact, so nothing needs a grid-wide barrier between simulations: a CTA owns its trees for the whole search
@@ -523,6 +654,10 @@ k_qmlp2(const MlpParams p_in, const TreeParams tp, const int n_sims, const int c
         uint32_t hfph = 0;    // bit T: parity of the next wait on hfree[T]
 #pragma unroll 1
         for (int s = 0; s < n_evals; ++s) {
+        if (TSM && nrows <= 32) {
+            q2_eval_rep<S, ACT, NL>(c, p, nrows, row_begin, lane, fullph, reinterpret_cast<float*>(sA), smt.part);
+            EP_STAMP(0);
+        } else
 #pragma unroll 1
         for (int t0 = 0; t0 < ntiles; t0 += 2) {
             const int nt = min(2, ntiles - t0);
